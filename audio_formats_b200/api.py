@@ -1,0 +1,400 @@
+"""ctypes mirror of include/l3b200.h.
+
+Names follow the reference's AudioStream (source/audioformats/stream.d): openFromMemory,
+openFromFile, readSamplesFloat, readSamplesDouble, seekPosition, tellPosition, getNumChannels,
+getLengthInFrames, getSamplerate, isError, errorMessage -- plus the batch entry point
+``Context.decode_scans`` the north star adds.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Sequence
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "libl3b200.so"
+_lib = None
+
+
+class L3BError(RuntimeError):
+    def __init__(self, code: int, msg: str = ""):
+        super().__init__(f"l3b200 error {code}: {msg}" if msg else f"l3b200 error {code}")
+        self.code = code
+
+
+E_PARAM, E_MEMORY, E_IOERROR, E_USER, E_DECODE, E_NOGPU, E_UNSUPPORTED = -1, -2, -3, -4, -5, -16, -17
+
+
+class GrchDesc(C.Structure):
+    _fields_ = [("bit_start", C.c_uint32), ("w1", C.c_uint32), ("w2", C.c_uint32), ("w3", C.c_uint32)]
+
+
+class StreamDesc(C.Structure):
+    _fields_ = [("maindata_off", C.c_uint64), ("maindata_bytes", C.c_uint32), ("n_granules", C.c_uint32),
+                ("first_grch", C.c_uint64), ("pcm_off", C.c_uint64), ("pcm_skip", C.c_uint64),
+                ("pcm_count", C.c_uint64), ("nch", C.c_uint8), ("sr_idx", C.c_uint8), ("mpeg1", C.c_uint8),
+                ("reserved", C.c_uint8), ("reserved2", C.c_uint32)]
+
+
+class Taps(C.Structure):
+    _fields_ = [("is_", C.c_void_p), ("iscf", C.c_void_p), ("ist_pos", C.c_void_p)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("maindata", C.c_void_p), ("maindata_bytes", C.c_uint64), ("grch", C.c_void_p), ("n_grch", C.c_uint64),
+                ("streams", C.c_void_p), ("n_streams", C.c_uint32), ("pcm", C.c_void_p), ("pcm_floats", C.c_uint64),
+                ("status", C.c_void_p), ("taps", C.c_void_p)]
+
+
+assert C.sizeof(GrchDesc) == 16 and C.sizeof(StreamDesc) == 56, (C.sizeof(GrchDesc), C.sizeof(StreamDesc))
+
+GRCH_DTYPE = np.dtype([("bit_start", "<u4"), ("w1", "<u4"), ("w2", "<u4"), ("w3", "<u4")])
+STREAM_DTYPE = np.dtype([("maindata_off", "<u8"), ("maindata_bytes", "<u4"), ("n_granules", "<u4"),
+                         ("first_grch", "<u8"), ("pcm_off", "<u8"), ("pcm_skip", "<u8"), ("pcm_count", "<u8"),
+                         ("nch", "u1"), ("sr_idx", "u1"), ("mpeg1", "u1"), ("reserved", "u1"), ("reserved2", "<u4")])
+assert STREAM_DTYPE.itemsize == 56
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def load_library():
+    """Load libl3b200.so.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise L3BError(E_NOGPU, f"{_LIB_PATH} is missing: run `python -m audio_formats_b200.build` "
+                                "(there is no CPU fallback)")
+    L = C.CDLL(str(_LIB_PATH))
+    vp, u8p = C.c_void_p, C.c_char_p
+    sig = {
+        "l3b_device_count": (C.c_int, []),
+        "l3b_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "l3b_ctx_destroy": (None, [vp]),
+        "l3b_last_error": (C.c_char_p, [vp]),
+        "l3b_decode_batch": (C.c_int, [vp, C.POINTER(Batch)]),
+        "l3b_batch_upload": (C.c_int, [vp, C.POINTER(Batch), C.POINTER(vp)]),
+        "l3b_batch_run": (C.c_int, [vp, vp]),
+        "l3b_batch_sync": (C.c_int, [vp]),
+        "l3b_batch_download": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64]),
+        "l3b_batch_download_taps": (C.c_int, [vp, vp, C.POINTER(Taps)]),
+        "l3b_batch_device_pcm": (vp, [vp]),
+        "l3b_batch_free": (None, [vp, vp]),
+        "l3b_batch_last_timing": (C.c_int, [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_int)]),
+        "l3b_ctx_cuda_stream": (vp, [vp]),
+        "l3b_scan_memory": (C.c_int, [u8p, C.c_size_t, C.POINTER(vp)]),
+        "l3b_scan_free": (None, [vp]),
+        "l3b_scan_channels": (C.c_int, [vp]),
+        "l3b_scan_samplerate": (C.c_int, [vp]),
+        "l3b_scan_error": (C.c_int, [vp]),
+        "l3b_scan_length_frames": (C.c_uint64, [vp]),
+        "l3b_scan_delivered_samples": (C.c_uint64, [vp]),
+        "l3b_scan_granules": (C.c_uint32, [vp]),
+        "l3b_scan_maindata_bytes": (C.c_uint64, [vp]),
+        "l3b_scan_maindata": (vp, [vp]),
+        "l3b_scan_descs": (vp, [vp]),
+        "l3b_scan_fill_stream_desc": (None, [vp, C.POINTER(StreamDesc)]),
+        "l3b_decode_scans": (C.c_int, [vp, C.POINTER(vp), C.c_uint32, C.POINTER(vp), C.POINTER(C.c_int32)]),
+        "l3b_stream_open_memory": (C.c_int, [vp, u8p, C.c_size_t, C.POINTER(vp)]),
+        "l3b_stream_open_file": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+        "l3b_stream_close": (None, [vp]),
+        "l3b_stream_num_channels": (C.c_int, [vp]),
+        "l3b_stream_length_frames": (C.c_int64, [vp]),
+        "l3b_stream_samplerate": (C.c_float, [vp]),
+        "l3b_stream_read_float": (C.c_int, [vp, vp, C.c_int]),
+        "l3b_stream_read_double": (C.c_int, [vp, vp, C.c_int]),
+        "l3b_stream_seek": (C.c_int, [vp, C.c_int]),
+        "l3b_stream_tell": (C.c_int, [vp]),
+        "l3b_stream_is_error": (C.c_int, [vp]),
+        "l3b_stream_error_message": (C.c_char_p, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here means the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    L._l3b_signatures = sig
+    _lib = L
+    return L
+
+
+def device_count() -> int:
+    return load_library().l3b_device_count()
+
+
+class Scan:
+    """Host prepass of one in-memory MP3 stream (frame sync, side info, reservoir slicing)."""
+
+    def __init__(self, data: bytes):
+        L = load_library()
+        h = C.c_void_p()
+        rc = L.l3b_scan_memory(data, len(data), C.byref(h))
+        if rc:
+            raise L3BError(rc, "scan failed (not an MP3 / unsupported layer)" if rc in (E_USER, E_UNSUPPORTED) else "")
+        self._h = h
+        self._L = L
+        self.channels = L.l3b_scan_channels(h)
+        self.samplerate = L.l3b_scan_samplerate(h)
+        self.length_frames = L.l3b_scan_length_frames(h)
+        self.delivered_samples = L.l3b_scan_delivered_samples(h)
+        self.granules = L.l3b_scan_granules(h)
+        self.error = L.l3b_scan_error(h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.l3b_scan_free(self._h)
+            self._h = None
+
+    @property
+    def descs(self) -> np.ndarray:
+        n = self.granules * self.channels
+        if not n:
+            return np.zeros(0, GRCH_DTYPE)
+        buf = (C.c_uint8 * (n * 16)).from_address(self._L.l3b_scan_descs(self._h))
+        return np.frombuffer(buf, dtype=GRCH_DTYPE).copy()
+
+    @property
+    def maindata(self) -> np.ndarray:
+        n = self._L.l3b_scan_maindata_bytes(self._h)
+        if not n:
+            return np.zeros(0, np.uint8)
+        buf = (C.c_uint8 * n).from_address(self._L.l3b_scan_maindata(self._h))
+        return np.frombuffer(buf, dtype=np.uint8).copy()
+
+    def stream_desc(self) -> StreamDesc:
+        d = StreamDesc()
+        self._L.l3b_scan_fill_stream_desc(self._h, C.byref(d))
+        return d
+
+
+class Context:
+    """One GPU context (one per GPU, one host thread at a time)."""
+
+    def __init__(self, device: int = 0):
+        L = load_library()
+        h = C.c_void_p()
+        rc = L.l3b_ctx_create(device, C.byref(h))
+        if rc:
+            raise L3BError(rc, (L.l3b_last_error(None) or b"").decode())
+        self._h, self._L, self.device = h, L, device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.l3b_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc:
+            raise L3BError(rc, (self._L.l3b_last_error(self._h) or b"").decode())
+
+    # ---- the batch entry point ---------------------------------------------------------------
+    def decode_scans(self, scans: Sequence[Scan]) -> list[np.ndarray]:
+        """Decode every stream of the batch on the GPU; returns one [frames, channels] float32 array each."""
+        n = len(scans)
+        outs = [np.empty(s.delivered_samples, dtype=np.float32) for s in scans]
+        hs = (C.c_void_p * n)(*[s._h for s in scans])
+        ps = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        st = (C.c_int32 * n)()
+        self._check(self._L.l3b_decode_scans(self._h, hs, n, ps, st))
+        return [o.reshape(-1, s.channels) for o, s in zip(outs, scans)]
+
+    def decode(self, datas: Sequence[bytes]) -> list[np.ndarray]:
+        return self.decode_scans([Scan(d) for d in datas])
+
+    # ---- resident batches (throughput work) ----------------------------------------------------
+    def upload(self, batch: "HostBatch") -> "ResidentBatch":
+        h = C.c_void_p()
+        self._check(self._L.l3b_batch_upload(self._h, C.byref(batch.c_batch(with_taps=batch.want_taps)), C.byref(h)))
+        return ResidentBatch(self, h, batch)
+
+
+class HostBatch:
+    """A batch assembled on the host from scans (what the D host hands to the shim)."""
+
+    def __init__(self, scans: Sequence[Scan], want_taps: bool = False, replicate: int = 1):
+        self.scans = list(scans)
+        self.want_taps = want_taps
+        blobs, descs = [], []
+        sd = np.zeros(len(scans) * replicate, dtype=STREAM_DTYPE)
+        off = grch = pcm = 0
+        k = 0
+        cache = [(s.maindata, s.descs, s.stream_desc()) for s in self.scans]
+        for _ in range(replicate):
+            for (md, ds, d0) in cache:
+                pad = (-len(md)) % 16 + 16
+                sd[k] = (off, len(md), d0.n_granules, grch, pcm, d0.pcm_skip, d0.pcm_count, d0.nch, d0.sr_idx, d0.mpeg1, 0, 0)
+                blobs.append(md)
+                blobs.append(np.zeros(pad, np.uint8))
+                descs.append(ds)
+                off += len(md) + pad
+                grch += len(ds)
+                pcm += d0.pcm_count
+                k += 1
+        self.blob = np.concatenate(blobs) if blobs else np.zeros(0, np.uint8)
+        self.descs = np.concatenate(descs) if descs else np.zeros(0, GRCH_DTYPE)
+        self.streams = sd
+        self.pcm_floats = int(pcm)
+        self.n_grch = int(grch)
+        self._taps = Taps()
+
+    def c_batch(self, pcm: np.ndarray | None = None, with_taps: bool = False) -> Batch:
+        b = Batch()
+        b.maindata, b.maindata_bytes = self.blob.ctypes.data, self.blob.size
+        b.grch, b.n_grch = self.descs.ctypes.data, self.n_grch
+        b.streams, b.n_streams = self.streams.ctypes.data, len(self.streams)
+        b.pcm = pcm.ctypes.data if pcm is not None else None
+        b.pcm_floats = self.pcm_floats
+        b.status = None
+        b.taps = C.cast(C.pointer(self._taps), C.c_void_p) if with_taps else None
+        return b
+
+
+class ResidentBatch:
+    def __init__(self, ctx: Context, h, host: HostBatch):
+        self.ctx, self._h, self.host = ctx, h, host
+
+    def run(self):
+        self.ctx._check(self.ctx._L.l3b_batch_run(self.ctx._h, self._h))
+
+    def sync(self):
+        self.ctx._check(self.ctx._L.l3b_batch_sync(self.ctx._h))
+
+    def timing(self):
+        ms = (C.c_float * 3)()
+        n = C.c_int()
+        self.ctx._check(self.ctx._L.l3b_batch_last_timing(self.ctx._h, C.byref(ms), C.byref(n)))
+        return list(ms), n.value
+
+    def download(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.host.pcm_floats - first if count is None else count
+        out = np.empty(count, np.float32)
+        self.ctx._check(self.ctx._L.l3b_batch_download(self.ctx._h, self._h, out.ctypes.data, first, count))
+        return out
+
+    def download_taps(self):
+        n = self.host.n_grch
+        is_ = np.empty((n, 576), np.int16)
+        iscf = np.empty((n, 40), np.uint8)
+        ist = np.empty((n, 40), np.uint8)
+        t = Taps(is_.ctypes.data, iscf.ctypes.data, ist.ctypes.data)
+        self.ctx._check(self.ctx._L.l3b_batch_download_taps(self.ctx._h, self._h, C.byref(t)))
+        return is_, iscf, ist
+
+    @property
+    def device_pcm_ptr(self) -> int:
+        return self.ctx._L.l3b_batch_device_pcm(self._h)
+
+    def free(self):
+        if self._h:
+            self.ctx._L.l3b_batch_free(self.ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def decode_batch_with_taps(ctx: Context, scans: Sequence[Scan]):
+    """Test helper: decode through l3b_decode_batch (host buffers in/out) and return
+    (list of pcm arrays, is[n_grch,576], iscf[n_grch,40], ist_pos[n_grch,40])."""
+    hb = HostBatch(scans, want_taps=True)
+    rb = ctx.upload(hb)
+    try:
+        rb.run()
+        rb.sync()
+        pcm = rb.download()
+        taps = rb.download_taps()
+    finally:
+        rb.free()
+    outs, off = [], 0
+    for s, sdesc in zip(scans, hb.streams):
+        n = int(sdesc["pcm_count"])
+        outs.append(pcm[off:off + n].reshape(-1, s.channels))
+        off += n
+    return outs, *taps
+
+
+class AudioStream:
+    """Mirror of audio-formats' AudioStream for MP3 input (stream.d:102-1925, MP3 arms only)."""
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx = ctx
+        self._own_ctx = False
+        self._h = None
+        self._L = load_library()
+
+    def _ensure_ctx(self):
+        if self._ctx is None:
+            self._ctx = Context(0)
+            self._own_ctx = True
+
+    def openFromMemory(self, data: bytes) -> "AudioStream":
+        self._ensure_ctx()
+        h = C.c_void_p()
+        rc = self._L.l3b_stream_open_memory(self._ctx._h, data, len(data), C.byref(h))
+        if rc:
+            raise L3BError(rc, "cannot open MP3 stream")
+        self._h = h
+        return self
+
+    def openFromFile(self, path: str) -> "AudioStream":
+        self._ensure_ctx()
+        h = C.c_void_p()
+        rc = self._L.l3b_stream_open_file(self._ctx._h, str(path).encode(), C.byref(h))
+        if rc:
+            raise L3BError(rc, "cannot open MP3 file")
+        self._h = h
+        return self
+
+    def close(self):
+        if self._h:
+            self._L.l3b_stream_close(self._h)
+            self._h = None
+        if self._own_ctx and self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def getNumChannels(self) -> int:
+        return self._L.l3b_stream_num_channels(self._h)
+
+    def getLengthInFrames(self) -> int:
+        return self._L.l3b_stream_length_frames(self._h)
+
+    def getSamplerate(self) -> float:
+        return self._L.l3b_stream_samplerate(self._h)
+
+    def isError(self) -> bool:
+        return bool(self._L.l3b_stream_is_error(self._h))
+
+    def errorMessage(self) -> str:
+        return (self._L.l3b_stream_error_message(self._h) or b"").decode()
+
+    def readSamplesFloat(self, frames: int) -> np.ndarray:
+        out = np.empty((frames, self.getNumChannels()), np.float32)
+        n = self._L.l3b_stream_read_float(self._h, out.ctypes.data, frames)
+        return out[:n]
+
+    def readSamplesDouble(self, frames: int) -> np.ndarray:
+        out = np.empty((frames, self.getNumChannels()), np.float64)
+        n = self._L.l3b_stream_read_double(self._h, out.ctypes.data, frames)
+        return out[:n]
+
+    def seekPosition(self, frame: int) -> bool:
+        return bool(self._L.l3b_stream_seek(self._h, frame))
+
+    def tellPosition(self) -> int:
+        return self._L.l3b_stream_tell(self._h)

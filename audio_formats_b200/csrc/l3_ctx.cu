@@ -1,0 +1,360 @@
+// l3_ctx.cu -- C-ABI layer 1 ("shim"): context, batch upload/run/download.  No CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/l3b200.h"
+#include "l3_device_tables.hpp"
+#include "l3_host.hpp"
+#include "l3_kernels.cuh"
+
+using namespace l3b;
+
+static thread_local std::string g_create_error;
+
+struct l3b_ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    void* d_tables = nullptr;  // one allocation holding every lookup table
+    DeviceTables t{};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_ms[3] = {0, 0, 0};
+    int last_launches = 0;
+    bool timed = false;
+};
+
+struct l3b_resident {
+    uint8_t* d_blob = nullptr;
+    l3b_grch_desc_t* d_grch = nullptr;
+    l3b_stream_desc_t* d_streams = nullptr;
+    uint4* d_is = nullptr;
+    uint8_t* d_sf = nullptr;
+    float* d_pcm = nullptr;
+    Tile* d_tiles[2] = {nullptr, nullptr};  // [0] stereo, [1] mono
+    uint32_t n_tiles[2] = {0, 0};
+    uint64_t n_grch = 0, pcm_floats = 0;
+    uint32_t n_streams = 0;
+    BatchParams params{};
+};
+
+#define CU_TRY(ctx, expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                  \
+            return e_ == cudaErrorMemoryAllocation ? L3B_E_MEMORY : L3B_E_NOGPU;              \
+        }                                                                                     \
+    } while (0)
+
+extern "C" {
+
+int l3b_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* l3b_last_error(const l3b_ctx_t* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int l3b_ctx_create(int device_id, l3b_ctx_t** out) {
+    if (!out) return L3B_E_PARAM;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU fallback)";
+        cudaGetLastError();
+        return L3B_E_NOGPU;
+    }
+    if (device_id < 0 || device_id >= n) { g_create_error = "device_id out of range"; return L3B_E_PARAM; }
+    l3b_ctx* c = new (std::nothrow) l3b_ctx();
+    if (!c) return L3B_E_MEMORY;
+    c->device = device_id;
+    auto fail = [&](const char* what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete c;
+        return L3B_E_NOGPU;
+    };
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    for (auto& ev : c->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
+
+    // lookup tables: one device allocation, sub-allocated at 256-byte granularity
+    HuffLut hl = build_huff_lut();
+    SfbMaps* sm = new SfbMaps();
+    build_sfb_maps(sm);
+    std::vector<uint8_t> img;
+    auto put = [&](const void* src, size_t bytes) {
+        size_t at = (img.size() + 255) & ~(size_t)255;
+        img.resize(at + bytes);
+        memcpy(img.data() + at, src, bytes);
+        return at;
+    };
+    size_t o_huff = put(hl.entries.data(), hl.entries.size() * 2);
+    size_t o_c1 = put(hl.count1, sizeof hl.count1);
+    size_t o_pair = put(sm->sfb_of_pair, sizeof sm->sfb_of_pair);
+    size_t o_w = put(sm->width, sizeof sm->width);
+    size_t o_s = put(sm->start, sizeof sm->start);
+    size_t o_perm = put(sm->perm, sizeof sm->perm);
+    size_t o_pow = put(L3_POW43, sizeof L3_POW43);
+    size_t o_win = put(L3_WIN, sizeof L3_WIN);
+    delete sm;
+    if ((e = cudaMalloc(&c->d_tables, img.size())) != cudaSuccess) return fail("cudaMalloc(tables)", e);
+    if ((e = cudaMemcpy(c->d_tables, img.data(), img.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy(tables)", e);
+    uint8_t* base = static_cast<uint8_t*>(c->d_tables);
+    c->t.huff = reinterpret_cast<const uint16_t*>(base + o_huff);
+    c->t.huff_entries = (uint32_t)hl.entries.size();
+    for (int i = 0; i < 16; i++) { c->t.huff_base[i] = hl.base[i]; c->t.huff_root[i] = hl.root_bits[i]; }
+    c->t.count1 = base + o_c1;
+    c->t.sfb_of_pair = base + o_pair;
+    c->t.sfb_width = base + o_w;
+    c->t.sfb_start = reinterpret_cast<const uint16_t*>(base + o_s);
+    c->t.perm = reinterpret_cast<const uint16_t*>(base + o_perm);
+    c->t.pow43 = reinterpret_cast<const float*>(base + o_pow);
+    c->t.win = reinterpret_cast<const float*>(base + o_win);
+    upload_constants();
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail("constant upload", e);
+    *out = c;
+    return 0;
+}
+
+void l3b_ctx_destroy(l3b_ctx_t* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->d_tables) cudaFree(c->d_tables);
+    for (auto& ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* l3b_ctx_cuda_stream(l3b_ctx_t* c) { return c ? (void*)c->stream : nullptr; }
+
+void l3b_batch_free(l3b_ctx_t* c, l3b_resident_t* r) {
+    if (!r) return;
+    if (c) cudaSetDevice(c->device);
+    cudaFree(r->d_blob);
+    cudaFree(r->d_grch);
+    cudaFree(r->d_streams);
+    cudaFree(r->d_is);
+    cudaFree(r->d_sf);
+    cudaFree(r->d_pcm);
+    cudaFree(r->d_tiles[0]);
+    cudaFree(r->d_tiles[1]);
+    delete r;
+}
+
+int l3b_batch_upload(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** out) {
+    if (!c || !b || !out) return L3B_E_PARAM;
+    *out = nullptr;
+    if (!b->n_streams || !b->streams || (b->n_grch && !b->grch) || (b->maindata_bytes && !b->maindata)) {
+        c->err = "empty or inconsistent batch";
+        return L3B_E_PARAM;
+    }
+    if (b->n_grch >= (1ull << 31)) { c->err = "more than 2^31 granule-channels in one batch; split it into waves"; return L3B_E_PARAM; }
+    // validate stream table and build the tile lists
+    std::vector<Tile> tiles[2];
+    uint64_t expect_grch = 0;
+    for (uint32_t i = 0; i < b->n_streams; i++) {
+        const l3b_stream_desc_t& s = b->streams[i];
+        if ((s.nch != 1 && s.nch != 2) || s.sr_idx > 7 || (s.maindata_off & 3) ||
+            s.maindata_off + s.maindata_bytes > b->maindata_bytes || s.first_grch != expect_grch ||
+            s.pcm_off + s.pcm_count > b->pcm_floats || s.pcm_skip + s.pcm_count > (uint64_t)s.n_granules * 576u * s.nch) {
+            c->err = "stream descriptor " + std::to_string(i) + " is inconsistent";
+            return L3B_E_PARAM;
+        }
+        expect_grch += (uint64_t)s.n_granules * s.nch;
+        if (!s.pcm_count) continue;
+        const uint64_t per = 576ull * s.nch;
+        uint32_t g0 = (uint32_t)(s.pcm_skip / per), g1 = (uint32_t)((s.pcm_skip + s.pcm_count + per - 1) / per);
+        for (uint32_t g = g0; g < g1; g += kTileGranules)
+            tiles[s.nch == 2 ? 0 : 1].push_back({i, g, std::min<uint32_t>(kTileGranules, g1 - g)});
+    }
+    if (expect_grch != b->n_grch) { c->err = "n_grch does not match the stream table"; return L3B_E_PARAM; }
+
+    CU_TRY(c, cudaSetDevice(c->device));
+    l3b_resident* r = new (std::nothrow) l3b_resident();
+    if (!r) return L3B_E_MEMORY;
+    r->n_grch = b->n_grch;
+    r->n_streams = b->n_streams;
+    r->pcm_floats = b->pcm_floats;
+    auto bail = [&](int code) { l3b_batch_free(c, r); return code; };
+#define CU_TRY_R(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            c->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                      \
+            return bail(e_ == cudaErrorMemoryAllocation ? L3B_E_MEMORY : L3B_E_NOGPU);        \
+        }                                                                                     \
+    } while (0)
+    const size_t blob_alloc = (size_t)b->maindata_bytes + 64;
+    CU_TRY_R(cudaMalloc(&r->d_blob, blob_alloc));
+    CU_TRY_R(cudaMemsetAsync(r->d_blob + b->maindata_bytes, 0, 64, c->stream));
+    if (b->maindata_bytes) CU_TRY_R(cudaMemcpyAsync(r->d_blob, b->maindata, b->maindata_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY_R(cudaMalloc(&r->d_grch, std::max<size_t>(16, b->n_grch * sizeof(l3b_grch_desc_t))));
+    if (b->n_grch) CU_TRY_R(cudaMemcpyAsync(r->d_grch, b->grch, b->n_grch * sizeof(l3b_grch_desc_t), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY_R(cudaMalloc(&r->d_streams, b->n_streams * sizeof(l3b_stream_desc_t)));
+    CU_TRY_R(cudaMemcpyAsync(r->d_streams, b->streams, b->n_streams * sizeof(l3b_stream_desc_t), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY_R(cudaMalloc(&r->d_is, std::max<size_t>(16, b->n_grch * kIsChunks * sizeof(uint4))));
+    CU_TRY_R(cudaMalloc(&r->d_sf, std::max<size_t>(16, b->n_grch * kSfRecBytes)));
+    CU_TRY_R(cudaMalloc(&r->d_pcm, std::max<size_t>(16, b->pcm_floats * sizeof(float))));
+    for (int k = 0; k < 2; k++) {
+        r->n_tiles[k] = (uint32_t)tiles[k].size();
+        if (!r->n_tiles[k]) continue;
+        CU_TRY_R(cudaMalloc(&r->d_tiles[k], tiles[k].size() * sizeof(Tile)));
+        CU_TRY_R(cudaMemcpyAsync(r->d_tiles[k], tiles[k].data(), tiles[k].size() * sizeof(Tile), cudaMemcpyHostToDevice, c->stream));
+    }
+    CU_TRY_R(cudaStreamSynchronize(c->stream));  // host vectors above go out of scope
+#undef CU_TRY_R
+    BatchParams& p = r->params;
+    p.blob = r->d_blob;
+    p.grch = r->d_grch;
+    p.n_grch = b->n_grch;
+    p.streams = r->d_streams;
+    p.n_streams = b->n_streams;
+    p.is = r->d_is;
+    p.sf = r->d_sf;
+    p.pcm = r->d_pcm;
+    p.zero_fill = b->taps ? 1 : 0;
+    p.t = c->t;
+    *out = r;
+    return 0;
+}
+
+int l3b_batch_run(l3b_ctx_t* c, l3b_resident_t* r) {
+    if (!c || !r) return L3B_E_PARAM;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaEventRecord(c->ev[0], c->stream));
+    launch_entropy(r->params, c->stream);
+    CU_TRY(c, cudaEventRecord(c->ev[1], c->stream));
+    launch_granule(r->params, r->d_tiles[0], r->n_tiles[0], r->d_tiles[1], r->n_tiles[1], c->stream, c->ev[2]);
+    CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+    CU_TRY(c, cudaGetLastError());
+    c->last_launches = (r->n_grch ? 1 : 0) + (r->n_tiles[0] ? 1 : 0) + (r->n_tiles[1] ? 1 : 0);
+    c->timed = true;
+    return 0;
+}
+
+int l3b_batch_sync(l3b_ctx_t* c) {
+    if (!c) return L3B_E_PARAM;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+int l3b_batch_last_timing(l3b_ctx_t* c, float ms[3], int* launches) {
+    if (!c || !c->timed) return L3B_E_PARAM;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaEventSynchronize(c->ev[3]));
+    for (int i = 0; i < 3; i++) CU_TRY(c, cudaEventElapsedTime(&c->last_ms[i], c->ev[i], c->ev[i + 1]));
+    if (ms) memcpy(ms, c->last_ms, sizeof c->last_ms);
+    if (launches) *launches = c->last_launches;
+    return 0;
+}
+
+int l3b_batch_download(l3b_ctx_t* c, l3b_resident_t* r, float* pcm_host, uint64_t first_float, uint64_t n_floats) {
+    if (!c || !r || (!pcm_host && n_floats) || first_float + n_floats > r->pcm_floats) return L3B_E_PARAM;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (n_floats)
+        CU_TRY(c, cudaMemcpyAsync(pcm_host, r->d_pcm + first_float, n_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int l3b_batch_download_taps(l3b_ctx_t* c, l3b_resident_t* r, const l3b_taps_t* taps) {
+    if (!c || !r || !taps) return L3B_E_PARAM;
+    if (!r->params.zero_fill) { c->err = "batch was uploaded without taps"; return L3B_E_PARAM; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    const uint64_t n = r->n_grch;
+    if (taps->is && n) CU_TRY(c, cudaMemcpyAsync(taps->is, r->d_is, n * 576 * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+    if ((taps->iscf || taps->ist_pos) && n) {
+        std::vector<uint8_t> rec(n * kSfRecBytes);
+        CU_TRY(c, cudaMemcpyAsync(rec.data(), r->d_sf, rec.size(), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        for (uint64_t i = 0; i < n; i++) {
+            if (taps->iscf) memcpy(taps->iscf + i * 40, rec.data() + i * kSfRecBytes, 40);
+            if (taps->ist_pos) memcpy(taps->ist_pos + i * 40, rec.data() + i * kSfRecBytes + 40, 40);
+        }
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void* l3b_batch_device_pcm(l3b_resident_t* r) { return r ? r->d_pcm : nullptr; }
+
+int l3b_decode_batch(l3b_ctx_t* c, const l3b_batch_t* b) {
+    if (!c || !b) return L3B_E_PARAM;
+    if (!b->pcm && b->pcm_floats) { c->err = "pcm destination missing"; return L3B_E_PARAM; }
+    l3b_resident_t* r = nullptr;
+    int rc = l3b_batch_upload(c, b, &r);
+    if (rc) return rc;
+    rc = l3b_batch_run(c, r);
+    if (!rc) rc = l3b_batch_download(c, r, b->pcm, 0, b->pcm_floats);
+    if (!rc && b->taps) rc = l3b_batch_download_taps(c, r, b->taps);
+    if (b->status)
+        for (uint32_t i = 0; i < b->n_streams; i++) b->status[i] = rc;
+    l3b_batch_free(c, r);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// layer 2: the batch entry point over scanned streams
+int l3b_decode_scans(l3b_ctx_t* c, l3b_scan_t* const* scans, uint32_t n, float* const* pcm, int32_t* status) {
+    if (!c || !scans || !n || !pcm) return L3B_E_PARAM;
+    std::vector<l3b_stream_desc_t> sd(n);
+    std::vector<l3b_grch_desc_t> descs;
+    std::vector<uint8_t> blob;
+    uint64_t pcm_total = 0;
+    size_t n_desc = 0, n_blob = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!scans[i]) return L3B_E_PARAM;
+        n_desc += scans[i]->r.prog.descs.size();
+        n_blob += ((scans[i]->r.prog.blob.size() + 15) & ~(size_t)15) + 16;
+    }
+    descs.reserve(n_desc);
+    blob.reserve(n_blob);
+    for (uint32_t i = 0; i < n; i++) {
+        const ScanResult& s = scans[i]->r;
+        l3b_scan_fill_stream_desc(scans[i], &sd[i]);
+        sd[i].maindata_off = blob.size();
+        sd[i].first_grch = descs.size();
+        sd[i].pcm_off = pcm_total;
+        pcm_total += s.pcm_count;
+        blob.insert(blob.end(), s.prog.blob.begin(), s.prog.blob.end());
+        blob.resize(((blob.size() + 15) & ~(size_t)15) + 16, 0);  // >= 16 zero bytes after every stream
+        descs.insert(descs.end(), s.prog.descs.begin(), s.prog.descs.end());
+    }
+    l3b_batch_t b{};
+    b.maindata = blob.data();
+    b.maindata_bytes = blob.size();
+    b.grch = descs.data();
+    b.n_grch = descs.size();
+    b.streams = sd.data();
+    b.n_streams = n;
+    b.pcm = nullptr;
+    b.pcm_floats = pcm_total;
+    l3b_resident_t* r = nullptr;
+    int rc = l3b_batch_upload(c, &b, &r);
+    if (!rc) rc = l3b_batch_run(c, r);
+    for (uint32_t i = 0; i < n && !rc; i++)
+        if (sd[i].pcm_count) {
+            cudaError_t e = cudaMemcpyAsync(pcm[i], r->d_pcm + sd[i].pcm_off, sd[i].pcm_count * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+            if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = L3B_E_NOGPU; }
+        }
+    if (!rc) rc = l3b_batch_sync(c);
+    if (status)
+        for (uint32_t i = 0; i < n; i++) status[i] = rc ? rc : scans[i]->r.last_error;
+    if (r) l3b_batch_free(c, r);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// l3_device_tables.hpp -- host-side construction of the lookup structures the kernels use.
+// Everything is derived at context creation from the canonical data in l3_tables_gen.h.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "l3_tables_gen.h"
+
+namespace l3b {
+
+// ---- Huffman decode LUT (our own layout) ---------------------------------------------------------
+// 16-bit entries, per book a root table of 2^root_bits entries followed by its sub-tables.
+//   leaf : bit15 = 0 : [len:4 @8][v1:4 @4][v0:4 @0]     len = bits consumed at THIS level (1..8, or 0 for the zero book)
+//   link : bit15 = 1 : [width-1:3 @12][offset:12 @0]    offset relative to the book's base
+// Book 15 (index L3_NBOOKS) is the all-zero book used by table_select 0/4/14 (minimp3.d:768: tabindex 0).
+struct HuffLut {
+    std::vector<uint16_t> entries;
+    uint16_t base[L3_NBOOKS + 1];
+    uint8_t root_bits[L3_NBOOKS + 1];
+    uint8_t count1[2][64];  // 6-bit peek -> flags<<4 | len
+};
+
+namespace detail {
+inline int find_code(int book, int len, uint32_t code) {
+    for (int s = 0; s < 256; s++)
+        if (L3_HLEN[book * 256 + s] == len && L3_HCODE[book * 256 + s] == code) return s;
+    return -1;
+}
+inline int longest_under(int book, uint32_t prefix, int plen) {
+    int m = 0;
+    for (int s = 0; s < 256; s++) {
+        int l = L3_HLEN[book * 256 + s];
+        if (l > plen && (L3_HCODE[book * 256 + s] >> (l - plen)) == prefix && l > m) m = l;
+    }
+    return m;
+}
+inline void build_level(int book, std::vector<uint16_t>& e, size_t book_base, uint32_t prefix, int plen, int width) {
+    size_t at = e.size();
+    e.resize(at + ((size_t)1 << width), 0);
+    for (uint32_t v = 0; v < (1u << width); v++) {
+        uint32_t bits = (prefix << width) | v;
+        bool done = false;
+        for (int l = plen + 1; l <= plen + width && !done; l++) {
+            int s = find_code(book, l, bits >> (plen + width - l));
+            if (s >= 0) {
+                e[at + v] = (uint16_t)(((l - plen) << 8) | ((s & 15) << 4) | (s >> 4));  // s = v0*16+v1
+                done = true;
+            }
+        }
+        if (!done) {
+            int rest = longest_under(book, bits, plen + width) - (plen + width);
+            int w = rest > 8 ? 8 : rest;
+            size_t child = e.size() - book_base;
+            e[at + v] = (uint16_t)(0x8000u | ((uint32_t)(w - 1) << 12) | (uint32_t)child);
+            build_level(book, e, book_base, bits, plen + width, w);
+        }
+    }
+}
+}  // namespace detail
+
+inline HuffLut build_huff_lut() {
+    HuffLut L;
+    for (int b = 0; b < L3_NBOOKS; b++) {
+        int rb = L3_BOOK_MAXLEN[b] < 8 ? L3_BOOK_MAXLEN[b] : 8;
+        L.base[b] = (uint16_t)L.entries.size();
+        L.root_bits[b] = (uint8_t)rb;
+        detail::build_level(b, L.entries, L.entries.size(), 0, 0, rb);
+    }
+    L.base[L3_NBOOKS] = (uint16_t)L.entries.size();
+    L.root_bits[L3_NBOOKS] = 1;
+    L.entries.push_back(0);
+    L.entries.push_back(0);
+    memset(L.count1, 0, sizeof L.count1);
+    for (int t = 0; t < 2; t++)
+        for (int v = 0; v < 64; v++)
+            for (int f = 0; f < 16; f++) {
+                int ln = L3_C1LEN[t * 16 + f];
+                if ((v >> (6 - ln)) == L3_C1CODE[t * 16 + f]) L.count1[t][v] = (uint8_t)((f << 4) | ln);
+            }
+    return L;
+}
+
+// ---- scalefactor-band maps -----------------------------------------------------------------------
+// kind: 0 long, 1 short, 2 mixed.   sfb_of_pair[row][kind][p] = sfb index of coefficients 2p, 2p+1.
+struct SfbMaps {
+    uint8_t sfb_of_pair[8][3][288];
+    uint8_t width[8][3][40];
+    uint16_t start[8][3][40];
+    uint16_t perm[8][2][576];  // [row][0 short / 1 mixed][k] = source index of output k for L3_reorder (minimp3.d:984-1000)
+};
+
+inline const uint8_t* sfb_row(int row, int kind) {
+    return kind == 0 ? L3_SFB_LONG + row * 23 : kind == 1 ? L3_SFB_SHORT + row * 40 : L3_SFB_MIXED + row * 40;
+}
+
+inline void build_sfb_maps(SfbMaps* M) {
+    memset(M, 0, sizeof *M);
+    for (int row = 0; row < 8; row++) {
+        for (int kind = 0; kind < 3; kind++) {
+            const uint8_t* t = sfb_row(row, kind);
+            int pos = 0;
+            for (int i = 0; i < 40 && (kind == 0 ? i < 23 : true) && t[i]; i++) {
+                M->width[row][kind][i] = t[i];
+                M->start[row][kind][i] = (uint16_t)pos;
+                for (int k = 0; k < t[i]; k += 2) M->sfb_of_pair[row][kind][(pos + k) >> 1] = (uint8_t)i;
+                pos += t[i];
+            }
+        }
+        const bool mpeg1 = row >= 5;
+        for (int mixed = 0; mixed < 2; mixed++) {
+            for (int k = 0; k < 576; k++) M->perm[row][mixed][k] = (uint16_t)k;
+            int n_long_bands = mixed ? (2 << (row == 1 ? 1 : 0)) : 0;  // minimp3.d:1218 (<<1 only at 8 kHz, sfb row 1)
+            int n_long_sfb = mixed ? (mpeg1 ? 8 : 6) : 0;
+            const uint8_t* sfb = sfb_row(row, mixed ? 2 : 1) + n_long_sfb;
+            int base = n_long_bands * 18, src = 0, dst = 0;
+            for (; *sfb; sfb += 3) {
+                int len = *sfb;
+                for (int i = 0; i < len; i++, src++) {
+                    for (int w = 0; w < 3; w++, dst++) {
+                        // the reference overruns its buffer for 8 kHz mixed blocks (UB); we stay inside 576
+                        if (base + dst < 576 && base + src + w * len < 576)
+                            M->perm[row][mixed][base + dst] = (uint16_t)(base + src + w * len);
+                    }
+                }
+                src += 2 * len;
+            }
+        }
+    }
+}
+
+}  // namespace l3b

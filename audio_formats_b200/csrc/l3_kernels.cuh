@@ -1,0 +1,71 @@
+// l3_kernels.cuh -- device code of the Layer III granule decode path (sm_100a).
+//
+// Two kernels:
+//   l3_entropy_kernel   one thread per granule-channel: scalefactor decode + Huffman decode
+//                       (minimp3.d:613-644, 659-712, 748-883) -> signed 16-bit quantised spectra.
+//                       Integer work only; these are the "bit-exact spectral intermediates".
+//   l3_granule_kernel   one CTA (one warp per channel) per run of consecutive granules of one stream:
+//                       requantisation (minimp3.d:714-746, 813-816, 846), MS/intensity stereo (:885-982),
+//                       short-block reorder (:984-1000), alias reduction (:1002-1020), IMDCT-36/12 with
+//                       overlap-add and frequency inversion (:1022-1168), DCT-32 matrixing (:1232-1298)
+//                       and the 512-tap window (:1305-1406), fused through shared memory and registers.
+//
+// Float arithmetic follows the reference's operation order exactly; this translation unit MUST be
+// compiled with -fmad=false (no FMA contraction) and default (IEEE) division/denormal settings so
+// that PCM is bit-identical to the un-fused scalar reference on x86-64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/l3b200.h"
+
+namespace l3b {
+
+constexpr int kSfRecBytes = 96;    // per granule-channel: iscf[40] ist_pos[40] nz_chunks(u16) pad
+constexpr int kIsChunks = 72;      // 576 int16 = 72 x 16 bytes
+constexpr int kTileGranules = 32;  // granules per CTA tile of the granule kernel (2-granule recompute halo)
+constexpr int kXrStride = 608;     // per-channel spectrum buffer: 576 natural layout / 32x19 padded layout
+constexpr int kDParity = 624;      // floats per (channel, slot parity) history array: 18 rows x 33 (+30 pad so that
+                                   // the two parities sit 16 banks apart)
+
+struct Tile {
+    uint32_t stream, g0, ng;
+};
+
+struct DeviceTables {
+    const uint16_t* huff;       // HuffLut::entries
+    uint32_t huff_entries;
+    uint16_t huff_base[16];
+    uint8_t huff_root[16];
+    const uint8_t* count1;      // [2][64]
+    const uint8_t* sfb_of_pair; // [8][3][288]
+    const uint8_t* sfb_width;   // [8][3][40]
+    const uint16_t* sfb_start;  // [8][3][40]
+    const uint16_t* perm;       // [8][2][576]
+    const float* pow43;         // [129]
+    const float* win;           // [240]  L3_WIN layout
+};
+
+struct BatchParams {
+    const uint8_t* blob;
+    const l3b_grch_desc_t* grch;
+    uint64_t n_grch;
+    const l3b_stream_desc_t* streams;
+    uint32_t n_streams;
+    uint4* is;       // [n_grch][72] packed int16x8
+    uint8_t* sf;     // [n_grch][96]
+    float* pcm;
+    int zero_fill;   // entropy kernel writes all 72 chunks (tap mode)
+    DeviceTables t;
+};
+
+__global__ void l3_entropy_kernel(BatchParams p);
+template <int NCH>
+__global__ void l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles);
+
+void launch_entropy(const BatchParams& p, cudaStream_t s);
+void launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
+                    uint32_t n_mono, cudaStream_t s, cudaEvent_t ev_mid);
+void upload_constants();
+
+}  // namespace l3b

@@ -1,0 +1,158 @@
+/* l3b200.h -- C-ABI of the B200-native MPEG-1/2/2.5 Layer III granule decode path.
+ *
+ * This is the drop-in boundary for audio-formats' MP3 hot path.  The reference has no FFI seam for
+ * MP3 (stream.d calls D functions of minimp3.d / minimp3_ex.d directly), so the boundary is placed
+ * where SURVEY.md 8b puts it:
+ *
+ *   layer 1  "shim"  (l3b_ctx_*, l3b_decode_batch)      replaces the granule work under
+ *                     mp3dec_decode_frame (minimp3.d:1492-1581): L3_decode (:1196) +
+ *                     mp3d_synth_granule (:1408) for every granule of every stream of a batch.
+ *   layer 2  "host"  (l3b_scan_*, l3b_stream_*)         is what the D host does before/around the
+ *                     shim: frame sync (minimp3.d:1436-1485), side-info parsing (:487-611),
+ *                     bit-reservoir slicing (:1170-1194) and the stream layer of minimp3_ex.d
+ *                     (index :566, seek :662, read :787, open :929) behind the AudioStream surface
+ *                     of stream.d (:115, :150, :429, :656, :1095, :1209).  No D compiler exists in
+ *                     the build image, so this layer is implemented in C++ in the same library and
+ *                     mirrored by the (uncompiled) D sources under audio_formats_b200/dhost/.
+ *
+ * Conventions: every function returns 0 or a negative MP3D_E_* style code (minimp3_ex.d:30-34),
+ * never throws, never calls back, never keeps caller memory after returning.  A context is bound to
+ * one GPU and must be used by one host thread at a time.  There is NO CPU fallback: every compute
+ * entry point fails with L3B_E_NOGPU when no CUDA device is usable.
+ */
+#ifndef L3B200_H
+#define L3B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L3B_OK 0
+#define L3B_E_PARAM (-1)     /* MP3D_E_PARAM   minimp3_ex.d:30 */
+#define L3B_E_MEMORY (-2)    /* MP3D_E_MEMORY  minimp3_ex.d:31 */
+#define L3B_E_IOERROR (-3)   /* MP3D_E_IOERROR minimp3_ex.d:32 */
+#define L3B_E_USER (-4)      /* MP3D_E_USER    minimp3_ex.d:33 (also: "not an MP3") */
+#define L3B_E_DECODE (-5)    /* MP3D_E_DECODE  minimp3_ex.d:34 */
+#define L3B_E_NOGPU (-16)    /* no usable CUDA device / kernel launch failed (ours) */
+#define L3B_E_UNSUPPORTED (-17) /* Layer I/II stream: outside this path */
+
+/* ------------------------------------------------------------------------------------------------
+ * Descriptors: what the host prepass hands to the GPU.
+ * One l3b_grch_desc_t per granule-channel (16 bytes); the nch descriptors of a granule are
+ * adjacent, granules of a stream are consecutive in decode order.  Packed copy of the fields of
+ * L3_gr_info_t (minimp3.d:189-196) plus the two things the sequential decoder carries implicitly:
+ * where the bits are, and whether decoder state was zeroed before this granule. */
+typedef struct {
+    uint32_t bit_start; /* first bit of this granule-channel's part2_3 data, relative to the stream's main-data blob */
+    uint32_t w1;        /* part_23_length[0:12] big_values[12:21] global_gain[21:29] block_type[29:31] mixed_block_flag[31] */
+    uint32_t w2;        /* scalefac_compress[0:9] table_select0[9:14] 1[14:19] 2[19:24] preflag[24] scalefac_scale[25]
+                           count1_table[26] scfsi[27:31] second_granule_of_frame[31] */
+    uint32_t w3;        /* region1_start/2[0:9] region2_start/2[9:18] subblock_gain0[18:21] 1[21:24] 2[24:27]
+                           header byte3 >> 4 (mode, mode_ext)[27:31] state_reset_before[31] */
+} l3b_grch_desc_t;
+
+/* One per stream of a batch. */
+typedef struct {
+    uint64_t maindata_off;   /* byte offset of this stream's main-data blob inside the batch blob (16-byte aligned) */
+    uint32_t maindata_bytes; /* valid bytes; the blob must be followed by >= 16 readable zero bytes */
+    uint32_t n_granules;     /* decodable granules, decode order */
+    uint64_t first_grch;     /* index of the stream's first descriptor in the batch descriptor array */
+    uint64_t pcm_off;        /* float offset of the stream's first delivered sample in the PCM output */
+    uint64_t pcm_skip;       /* interleaved samples to drop from the front of the decoded signal (encoder delay, minimp3_ex.d:862-867) */
+    uint64_t pcm_count;      /* interleaved samples to deliver after the skip (padding trim, minimp3_ex.d:869-873) */
+    uint8_t nch;             /* 1 or 2 */
+    uint8_t sr_idx;          /* row of the sfb tables, minimp3.d:523 */
+    uint8_t mpeg1;           /* 1: MPEG-1 (2 granules/frame), 0: MPEG-2 / 2.5 LSF */
+    uint8_t reserved;
+    uint32_t reserved2;
+} l3b_stream_desc_t;
+
+/* Optional test taps (all device-side intermediates copied back; NULL = not wanted).
+ * Layout: [granule-channel descriptor index][...]. */
+typedef struct {
+    int16_t* is;      /* [n_grch][576] signed quantised values (the reference's fused Huffman never materialises these) */
+    uint8_t* iscf;    /* [n_grch][40]  integer scalefactors after subblock_gain / preflag (minimp3.d:694-712) */
+    uint8_t* ist_pos; /* [n_grch][40]  intensity positions as left by L3_decode_scalefactors */
+} l3b_taps_t;
+
+typedef struct {
+    const uint8_t* maindata;          /* batch blob: HOST memory (copied in) */
+    uint64_t maindata_bytes;
+    const l3b_grch_desc_t* grch;      /* HOST */
+    uint64_t n_grch;
+    const l3b_stream_desc_t* streams; /* HOST */
+    uint32_t n_streams;
+    float* pcm;                       /* HOST destination, interleaved float, sum(pcm_count) floats laid out by pcm_off */
+    uint64_t pcm_floats;
+    int32_t* status;                  /* HOST, optional [n_streams]: 0 or negative code per stream */
+    const l3b_taps_t* taps;           /* optional */
+} l3b_batch_t;
+
+typedef struct l3b_ctx l3b_ctx_t;
+
+/* -------- layer 1: shim ---------------------------------------------------------------------- */
+int l3b_device_count(void);
+int l3b_ctx_create(int device_id, l3b_ctx_t** out);
+void l3b_ctx_destroy(l3b_ctx_t* ctx);
+const char* l3b_last_error(const l3b_ctx_t* ctx); /* ctx may be NULL: last error of a failed create */
+
+/* Decode a whole batch, host buffers in / host buffers out (H2D + kernels + D2H inside). */
+int l3b_decode_batch(l3b_ctx_t* ctx, const l3b_batch_t* batch);
+
+/* Device-resident variant used for throughput work: upload once, run many times, read back on demand.
+ * l3b_batch_upload keeps descriptors + blob on the GPU and allocates the PCM buffer there. */
+typedef struct l3b_resident l3b_resident_t;
+int l3b_batch_upload(l3b_ctx_t* ctx, const l3b_batch_t* batch, l3b_resident_t** out);
+int l3b_batch_run(l3b_ctx_t* ctx, l3b_resident_t* r);                      /* async on the context stream */
+int l3b_batch_sync(l3b_ctx_t* ctx);
+int l3b_batch_download(l3b_ctx_t* ctx, l3b_resident_t* r, float* pcm_host, uint64_t first_float, uint64_t n_floats);
+int l3b_batch_download_taps(l3b_ctx_t* ctx, l3b_resident_t* r, const l3b_taps_t* taps);
+void* l3b_batch_device_pcm(l3b_resident_t* r);                              /* raw device pointer (for checksums/tests) */
+void l3b_batch_free(l3b_ctx_t* ctx, l3b_resident_t* r);
+/* CUDA-event timing of the most recent l3b_batch_run: total and per-kernel milliseconds
+ * (ms[0] entropy kernel, ms[1] granule kernel stereo, ms[2] granule kernel mono), launches issued. */
+int l3b_batch_last_timing(l3b_ctx_t* ctx, float ms[3], int* launches);
+void* l3b_ctx_cuda_stream(l3b_ctx_t* ctx);
+
+/* -------- layer 2: host prepass + AudioStream surface ------------------------------------------ */
+typedef struct l3b_scan l3b_scan_t;
+
+/* Frame sync + side-info parse + reservoir slicing of a whole in-memory stream, following the
+ * reference's open/read loop exactly (which frames yield PCM, resets, delay/padding trim). */
+int l3b_scan_memory(const uint8_t* data, size_t size, l3b_scan_t** out);
+void l3b_scan_free(l3b_scan_t* s);
+int l3b_scan_channels(const l3b_scan_t* s);
+int l3b_scan_samplerate(const l3b_scan_t* s);
+int l3b_scan_error(const l3b_scan_t* s);                 /* sticky decode error met while scanning (0 = none) */
+uint64_t l3b_scan_length_frames(const l3b_scan_t* s);    /* AudioStream.getLengthInFrames (stream.d:1738) */
+uint64_t l3b_scan_delivered_samples(const l3b_scan_t* s);/* interleaved samples a read-to-end delivers */
+uint32_t l3b_scan_granules(const l3b_scan_t* s);
+uint64_t l3b_scan_maindata_bytes(const l3b_scan_t* s);
+const uint8_t* l3b_scan_maindata(const l3b_scan_t* s);
+const l3b_grch_desc_t* l3b_scan_descs(const l3b_scan_t* s);
+void l3b_scan_fill_stream_desc(const l3b_scan_t* s, l3b_stream_desc_t* out); /* offsets left 0 */
+
+/* Batch entry point the D host adds next to AudioStream: decode n scanned streams in one go.
+ * pcm[i] must have room for l3b_scan_delivered_samples(scans[i]) floats. */
+int l3b_decode_scans(l3b_ctx_t* ctx, l3b_scan_t* const* scans, uint32_t n, float* const* pcm, int32_t* status);
+
+/* AudioStream mirror (names follow stream.d). */
+typedef struct l3b_stream l3b_stream_t;
+int l3b_stream_open_memory(l3b_ctx_t* ctx, const uint8_t* data, size_t size, l3b_stream_t** out); /* stream.d:150 (copies input) */
+int l3b_stream_open_file(l3b_ctx_t* ctx, const char* path, l3b_stream_t** out);                   /* stream.d:115 */
+void l3b_stream_close(l3b_stream_t* s);
+int l3b_stream_num_channels(const l3b_stream_t* s);      /* stream.d:396 */
+int64_t l3b_stream_length_frames(const l3b_stream_t* s); /* stream.d:402 */
+float l3b_stream_samplerate(const l3b_stream_t* s);      /* stream.d:412 */
+int l3b_stream_read_float(l3b_stream_t* s, float* out, int frames);   /* stream.d:429: frames read; 0 on error (see is_error) */
+int l3b_stream_read_double(l3b_stream_t* s, double* out, int frames); /* stream.d:656 */
+int l3b_stream_seek(l3b_stream_t* s, int frame);         /* stream.d:1095: 1 = ok, 0 = refused */
+int l3b_stream_tell(const l3b_stream_t* s);              /* stream.d:1209 */
+int l3b_stream_is_error(const l3b_stream_t* s);          /* stream.d:295 */
+const char* l3b_stream_error_message(const l3b_stream_t* s); /* stream.d:316 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
