@@ -551,12 +551,18 @@ __global__ void __launch_bounds__(32 * NCH) l3_granule_kernel(BatchParams p, con
             float* L = s_xr[0];
             float* R = s_xr[1];
             if (istereo) {
+                // L3_intensity_stereo works on channel 0's band layout (gr_info of ch 0, minimp3.d:1209) and on
+                // channel 1's scalefac_compress (gr[1], minimp3.d:981)
+                const Desc d0 = load_desc(p.grch + S.first_grch + (uint64_t)g * NCH + 0);
                 const Desc d1 = load_desc(p.grch + S.first_grch + (uint64_t)g * NCH + 1);
+                const int kind0 = d0.kind();
+                const int n_long_sfb0 = kind0 == 0 ? 22 : (kind0 == 1 ? 0 : (mpeg1 ? 8 : 6));
+                const int n_sfb0 = n_long_sfb0 + (kind0 == 0 ? 0 : (kind0 == 1 ? 39 : 30));
                 if (ch == 0) {
                     // L3_stereo_top_band: last sfb (per window) of the right channel holding a non-zero value
                     int mb0 = -1, mb1 = -1, mb2 = -1;
-                    for (int i = lane; i < n_sfb; i += 32) {
-                        const int off = s_sfbo[kind][i], wdt = s_sfbw[kind][i];
+                    for (int i = lane; i < n_sfb0; i += 32) {
+                        const int off = s_sfbo[kind0][i], wdt = s_sfbw[kind0][i];
                         bool nz = false;
                         for (int k = 0; k < wdt; k++) nz |= (R[off + k] != 0.0f);
                         if (nz) { int c = i % 3; if (c == 0) mb0 = max(mb0, i); else if (c == 1) mb1 = max(mb1, i); else mb2 = max(mb2, i); }
@@ -567,13 +573,13 @@ __global__ void __launch_bounds__(32 * NCH) l3_granule_kernel(BatchParams p, con
                         mb1 = max(mb1, __shfl_xor_sync(0xffffffffu, mb1, sft));
                         mb2 = max(mb2, __shfl_xor_sync(0xffffffffu, mb2, sft));
                     }
-                    if (n_long_sfb) mb0 = mb1 = mb2 = max(max(mb0, mb1), mb2);
+                    if (n_long_sfb0) mb0 = mb1 = mb2 = max(max(mb0, mb1), mb2);
                     if (lane == 0) {
-                        const int max_blocks = kind == 0 ? 1 : 3;
+                        const int max_blocks = kind0 == 0 ? 1 : 3;
                         const int default_pos = mpeg1 ? 3 : 0;
                         const int mb[3] = {mb0, mb1, mb2};
                         for (int i = 0; i < max_blocks; i++) {
-                            int itop = n_sfb - max_blocks + i, prev = itop - max_blocks;
+                            int itop = n_sfb0 - max_blocks + i, prev = itop - max_blocks;
                             s_ist[itop] = (uint8_t)(mb[i] >= prev ? default_pos : s_ist[prev]);
                         }
                         s_maxband[0] = mb0; s_maxband[1] = mb1; s_maxband[2] = mb2;
@@ -582,7 +588,7 @@ __global__ void __launch_bounds__(32 * NCH) l3_granule_kernel(BatchParams p, con
                     // L3_stereo_process: per-sfb decision and gains
                     const unsigned max_pos = mpeg1 ? 7u : 64u;
                     const int mpeg2_sh = d1.scalefac_compress() & 1;
-                    for (int i = lane; i < n_sfb; i += 32) {
+                    for (int i = lane; i < n_sfb0; i += 32) {
                         const unsigned ipos = s_ist[i];
                         uint8_t md = 0;
                         if (i > s_maxband[i % 3] && ipos < max_pos) {
@@ -608,7 +614,7 @@ __global__ void __launch_bounds__(32 * NCH) l3_granule_kernel(BatchParams p, con
 #pragma unroll
                 for (int m = 0; m < 9; m++) {
                     const int k = ch * 288 + lane + 32 * m;
-                    const int sfb = s_sfbpair[kind][k >> 1];
+                    const int sfb = s_sfbpair[kind0][k >> 1];
                     const int md = s_smode[sfb];
                     const float a = L[k], b = R[k];
                     if (md == 1) { R[k] = a * s_kr[sfb]; L[k] = a * s_kl[sfb]; }

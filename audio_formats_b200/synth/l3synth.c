@@ -522,6 +522,17 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
             int zero_above[2] = {-1, -1};
             int bt[2], mx[2];
             for (int ch = 0; ch < nch; ch++) bt[ch] = next_block_type(p, &cs, &rng, ch, &mx[ch]);
+            if (nch == 2 && p->stereo_mode >= 2) {
+                /* With intensity stereo the reference walks channel 0's band layout over channel 1's ist_pos
+                 * array (minimp3.d:963-981); if channel 0 has more bands than channel 1 transmitted it reads
+                 * uninitialised scratch (UB upstream).  Encoders that use intensity stereo keep both channels
+                 * on the same block type, and so do we. */
+                bt[1] = bt[0];
+                mx[1] = mx[0];
+                cs.bt_state[1] = cs.bt_state[0];
+                cs.short_left[1] = cs.short_left[0];
+                cs.mixed_run[1] = cs.mixed_run[0];
+            }
             if (nch == 2 && (mode_ext & 1)) {
                 /* intensity stereo needs an all-zero top in channel 1 */
                 zero_above[1] = 2 * (int)(40 + rng_below(&rng, 200));

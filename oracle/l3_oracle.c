@@ -1067,6 +1067,10 @@ int l3o_decode_frame(l3o_dec_t* dec, const uint8_t* mp3, int mp3_bytes, float* p
             l3o_init(dec);
             return 0;
         }
+        /* The reference's scratch is an uninitialised stack object; ist_pos entries a granule does not
+         * transmit are read by L3_intensity_stereo when channel 0 has more bands than channel 1 (UB upstream).
+         * The oracle zeroes them per frame so that it is deterministic. */
+        memset(scratch.ist_pos, 0, sizeof scratch.ist_pos);
         success = restore_reservoir(dec, bs_frame, &scratch, main_data_begin);
         if (g_timers_on) t_timer[0] += now_s() - t0;
         if (success) {
