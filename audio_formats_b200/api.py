@@ -78,13 +78,14 @@ def load_library():
         "l3b_last_error": (C.c_char_p, [vp]),
         "l3b_decode_batch": (C.c_int, [vp, C.POINTER(Batch)]),
         "l3b_batch_upload": (C.c_int, [vp, C.POINTER(Batch), C.POINTER(vp)]),
+        "l3b_batch_reupload": (C.c_int, [vp, vp, C.POINTER(Batch)]),
         "l3b_batch_run": (C.c_int, [vp, vp]),
         "l3b_batch_sync": (C.c_int, [vp]),
         "l3b_batch_download": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64]),
         "l3b_batch_download_taps": (C.c_int, [vp, vp, C.POINTER(Taps)]),
         "l3b_batch_device_pcm": (vp, [vp]),
         "l3b_batch_free": (None, [vp, vp]),
-        "l3b_batch_last_timing": (C.c_int, [vp, C.POINTER(C.c_float * 3), C.POINTER(C.c_int)]),
+        "l3b_batch_timing": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float * 3), C.POINTER(C.c_int)]),
         "l3b_ctx_cuda_stream": (vp, [vp]),
         "l3b_scan_memory": (C.c_int, [u8p, C.c_size_t, C.POINTER(vp)]),
         "l3b_scan_free": (None, [vp]),
@@ -189,6 +190,10 @@ class Context:
     def __del__(self):
         self.close()
 
+    @property
+    def cuda_stream(self) -> int:
+        return self._L.l3b_ctx_cuda_stream(self._h)
+
     def _check(self, rc: int):
         if rc:
             raise L3BError(rc, (self._L.l3b_last_error(self._h) or b"").decode())
@@ -262,13 +267,21 @@ class ResidentBatch:
     def run(self):
         self.ctx._check(self.ctx._L.l3b_batch_run(self.ctx._h, self._h))
 
+    def reupload(self):
+        """Per-step H2D of the inputs (blob + descriptors) into the resident device buffers."""
+        self.ctx._check(self.ctx._L.l3b_batch_reupload(self.ctx._h, self._h, C.byref(self.host.c_batch())))
+
+    def download_into(self, ptr: int, first: int, count: int):
+        self.ctx._check(self.ctx._L.l3b_batch_download(self.ctx._h, self._h, ptr, first, count))
+
     def sync(self):
         self.ctx._check(self.ctx._L.l3b_batch_sync(self.ctx._h))
 
-    def timing(self):
+    def timing(self, last_runs: int = 1):
+        """(ms summed over the last runs [entropy, granule stereo, granule mono], kernels launched)."""
         ms = (C.c_float * 3)()
         n = C.c_int()
-        self.ctx._check(self.ctx._L.l3b_batch_last_timing(self.ctx._h, C.byref(ms), C.byref(n)))
+        self.ctx._check(self.ctx._L.l3b_batch_timing(self.ctx._h, last_runs, C.byref(ms), C.byref(n)))
         return list(ms), n.value
 
     def download(self, first: int = 0, count: int | None = None) -> np.ndarray:

@@ -23,10 +23,10 @@ struct l3b_ctx {
     std::string err;
     void* d_tables = nullptr;  // one allocation holding every lookup table
     DeviceTables t{};
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float last_ms[3] = {0, 0, 0};
+    static constexpr int kRing = 64;  // runs whose per-kernel events are kept
+    cudaEvent_t ev[kRing * 4] = {};
+    uint64_t runs = 0;
     int last_launches = 0;
-    bool timed = false;
 };
 
 struct l3b_resident {
@@ -229,17 +229,31 @@ int l3b_batch_upload(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** out) {
     return 0;
 }
 
+int l3b_batch_reupload(l3b_ctx_t* c, l3b_resident_t* r, const l3b_batch_t* b) {
+    if (!c || !r || !b) return L3B_E_PARAM;
+    if (b->n_grch != r->n_grch || b->n_streams != r->n_streams || b->pcm_floats != r->pcm_floats) {
+        c->err = "reupload: batch shape differs from the resident batch";
+        return L3B_E_PARAM;
+    }
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (b->maindata_bytes) CU_TRY(c, cudaMemcpyAsync(r->d_blob, b->maindata, b->maindata_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (b->n_grch) CU_TRY(c, cudaMemcpyAsync(r->d_grch, b->grch, b->n_grch * sizeof(l3b_grch_desc_t), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(r->d_streams, b->streams, b->n_streams * sizeof(l3b_stream_desc_t), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
 int l3b_batch_run(l3b_ctx_t* c, l3b_resident_t* r) {
     if (!c || !r) return L3B_E_PARAM;
     CU_TRY(c, cudaSetDevice(c->device));
-    CU_TRY(c, cudaEventRecord(c->ev[0], c->stream));
+    cudaEvent_t* ev = c->ev + 4 * (c->runs % l3b_ctx::kRing);
+    CU_TRY(c, cudaEventRecord(ev[0], c->stream));
     launch_entropy(r->params, c->stream);
-    CU_TRY(c, cudaEventRecord(c->ev[1], c->stream));
-    launch_granule(r->params, r->d_tiles[0], r->n_tiles[0], r->d_tiles[1], r->n_tiles[1], c->stream, c->ev[2]);
-    CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+    CU_TRY(c, cudaEventRecord(ev[1], c->stream));
+    launch_granule(r->params, r->d_tiles[0], r->n_tiles[0], r->d_tiles[1], r->n_tiles[1], c->stream, ev[2]);
+    CU_TRY(c, cudaEventRecord(ev[3], c->stream));
     CU_TRY(c, cudaGetLastError());
     c->last_launches = (r->n_grch ? 1 : 0) + (r->n_tiles[0] ? 1 : 0) + (r->n_tiles[1] ? 1 : 0);
-    c->timed = true;
+    c->runs++;
     return 0;
 }
 
@@ -251,13 +265,23 @@ int l3b_batch_sync(l3b_ctx_t* c) {
     return 0;
 }
 
-int l3b_batch_last_timing(l3b_ctx_t* c, float ms[3], int* launches) {
-    if (!c || !c->timed) return L3B_E_PARAM;
+int l3b_batch_timing(l3b_ctx_t* c, int last_runs, float ms[3], int* launches) {
+    if (!c || !c->runs || last_runs < 1) return L3B_E_PARAM;
+    if ((uint64_t)last_runs > c->runs) last_runs = (int)c->runs;
+    if (last_runs > l3b_ctx::kRing) last_runs = l3b_ctx::kRing;
     CU_TRY(c, cudaSetDevice(c->device));
-    CU_TRY(c, cudaEventSynchronize(c->ev[3]));
-    for (int i = 0; i < 3; i++) CU_TRY(c, cudaEventElapsedTime(&c->last_ms[i], c->ev[i], c->ev[i + 1]));
-    if (ms) memcpy(ms, c->last_ms, sizeof c->last_ms);
-    if (launches) *launches = c->last_launches;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    float sum[3] = {0, 0, 0};
+    for (int k = 0; k < last_runs; k++) {
+        cudaEvent_t* ev = c->ev + 4 * ((c->runs - 1 - k) % l3b_ctx::kRing);
+        for (int i = 0; i < 3; i++) {
+            float t = 0;
+            CU_TRY(c, cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+            sum[i] += t;
+        }
+    }
+    if (ms) memcpy(ms, sum, sizeof sum);
+    if (launches) *launches = c->last_launches * last_runs;
     return 0;
 }
 

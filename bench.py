@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- MP3 (MPEG-1 Layer III) batch decode throughput, audio-seconds decoded per second.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU decoder on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic streams.  At N=1 the workload is
+BASELINE.json configs[1]: 1,024 synthetic 60 s 44.1 kHz stereo 128 kbps MPEG-1 Layer III long-block
+streams (seeds 0..1023).  N>1: streams shard by file, 1,024 streams per GPU, no collective (weak scaling).
+
+`value`   device-resident throughput: bitstreams + descriptors already in HBM, entropy + granule kernels.
+`e2e`     MP3 bytes in host memory -> float PCM in pinned host memory through the public batch API:
+          host prepass (frame sync / side info / reservoir slicing, all host threads) + H2D + kernels + D2H.
+`roofline` of the dominant (granule) kernel; `cpu_baseline`: the C oracle (port of the D reference, which
+          cannot be built here: no D compiler) on the host cores, timed in the same run.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+METRIC = "mp3_batch_decode_audio_seconds_per_second"
+UNIT = "audio-s/s"
+FLOPS_PER_GRCH = 32734          # SURVEY.md 8d / BASELINE.md 3: float add/sub/mul per granule-channel
+FP32_NOMINAL_TFLOPS = 74.45     # 148 SM x 128 lanes x 2 x 1.965 GHz (not measured by the driver)
+HBM_FALLBACK_GBS = 6650.0       # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def gen_streams(seeds, seconds, threads):
+    from audio_formats_b200 import synth
+    synth.build()
+
+    def one(seed):
+        return synth.generate(synth.config2_params(seed, seconds))
+
+    with ThreadPoolExecutor(threads) as ex:
+        return list(ex.map(one, seeds))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_decode_throughput(streams, threads, min_seconds=0.0):
+    """Decode `streams` with the oracle's transcode loop on `threads` host threads; returns (audio_s, wall_s)."""
+    import oracle
+    oracle.build()
+    oracle.lib()
+
+    def one(st):
+        n, nch, hz, _ = oracle.transcode_loop(st.data, 1024, keep=False)
+        return n / hz
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        audio = sum(ex.map(one, streams))
+    return audio, time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path on the host cores.  The D decoder cannot
+    be built in this image (no dmd/ldc2/gdc), so this runs the C port (oracle/), all host threads."""
+    if rank != 0:
+        return
+    threads = host_threads()
+    probe = gen_streams(range(min(threads, 8)), args.seconds, threads)
+    a, w = cpu_decode_throughput(probe, threads)
+    per_stream_s = w * min(threads, len(probe)) / max(1, len(probe))  # thread-seconds per stream
+    n_sample = int(max(threads, min(args.streams, args.ref_step_seconds * threads / max(per_stream_s, 1e-6))))
+    n_sample = (n_sample // threads) * threads or threads
+    streams = gen_streams(range(n_sample), args.seconds, threads)
+    for _ in range(args.warmup):
+        cpu_decode_throughput(streams, threads)
+    audio = wall = 0.0
+    for _ in range(args.steps):
+        a, w = cpu_decode_throughput(streams, threads)
+        audio += a; wall += w
+    value = audio / wall
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, n_sample, "bounded sample of the same seeded streams"),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{n_sample} streams x {args.seconds:g} s per step, transcode loop (1024-frame reads)",
+                             "note": "C restatement of the reference's D decoder; the D build itself could not be produced here"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_streams, note=""):
+    return {"workload": f"BASELINE.json configs[1]: {n_streams} synthetic {args.seconds:g} s 44.1 kHz stereo 128 kbps "
+                        f"MPEG-1 Layer III long-block streams per GPU (seeds rank*streams+i)",
+            "streams_per_gpu": n_streams, "seconds_per_stream": args.seconds, "sharding": "by file, no collective",
+            "l2": "inputs larger than L2 (no flush needed)", **({"note": note} if note else {})}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
+    ap.add_argument("--seconds", type=float, default=60.0, help="seconds per stream")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-step-seconds", type=float, default=6.0)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import audio_formats_b200 as af
+    from audio_formats_b200 import api
+    from audio_formats_b200 import build as b
+    if b.needs_build():
+        b.build()
+    if not torch.cuda.is_available() or af.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    threads = max(1, host_threads() // max(1, min(world, 8)))
+    t0 = time.perf_counter()
+    streams = gen_streams(range(rank * args.streams, (rank + 1) * args.streams), args.seconds, threads)
+    t_gen = time.perf_counter() - t0
+    datas = [s.data for s in streams]
+
+    def prepass():
+        with ThreadPoolExecutor(threads) as ex:
+            return list(ex.map(af.Scan, datas))
+
+    t0 = time.perf_counter()
+    scans = prepass()
+    t_scan = time.perf_counter() - t0
+    audio_s = sum(s.delivered_samples / s.channels / s.samplerate for s in scans)
+    n_grch = sum(s.granules * s.channels for s in scans)
+
+    ctx = af.Context(local)
+    hb = api.HostBatch(scans)
+    # inputs live in pinned host memory (H2D source of every e2e step)
+    pin_blob = torch.empty(hb.blob.size, dtype=torch.uint8).pin_memory()
+    pin_blob.numpy()[:] = hb.blob
+    pin_desc = torch.empty(hb.descs.size * 16, dtype=torch.uint8).pin_memory()
+    pin_desc.numpy()[:] = hb.descs.view(np.uint8)
+    hb.blob = pin_blob.numpy()
+    hb.descs = pin_desc.numpy().view(api.GRCH_DTYPE)
+    rb = ctx.upload(hb)
+    ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=torch.device("cuda", local))
+
+    # ---- device-resident timing: W warm-up steps, then EXACTLY K timed steps ------------------------
+    for _ in range(args.warmup):
+        rb.run()
+    rb.sync()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
+    for _ in range(args.steps):
+        rb.run()
+    ev1.record(ext)
+    rb.sync()
+    barrier()
+    clocks = sampler.stop()
+    step_ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    kern_ms, launches = rb.timing(min(args.steps, 64))
+    nk = min(args.steps, 64)
+    total_audio = sum_over_ranks(audio_s)
+    value = total_audio / (step_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (granule kernel) ----------------------------------------------
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+    gran_ms = (kern_ms[1] + kern_ms[2]) / nk
+    ent_ms = kern_ms[0] / nk
+    pcm_bytes = hb.pcm_floats * 4
+    alg_bytes = pcm_bytes + int(hb.blob.size)          # PCM out + bitstream in (descriptors separate)
+    achieved_gbs = alg_bytes / (gran_ms * 1e-3) / 1e9
+    fp32_tflops = n_grch * FLOPS_PER_GRCH / (gran_ms * 1e-3) / 1e12
+    hbm_ceiling = hbm_peak * 1e9 / (alg_bytes / audio_s)              # audio-s/s if HBM-bound
+    fp32_ceiling = FP32_NOMINAL_TFLOPS * 1e12 / (n_grch * FLOPS_PER_GRCH / audio_s)
+    roofline = {"bound": "hbm", "kernel": "l3_granule_kernel<2>", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "peak_source": "measured" if peaks else "fallback", "traffic": None,
+                "ms_per_launch": gran_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "fp32": {"achieved_tflops": fp32_tflops, "peak_tflops_nominal": FP32_NOMINAL_TFLOPS,
+                         "frac": fp32_tflops / FP32_NOMINAL_TFLOPS,
+                         "note": "flops counted un-fused (32,734 per granule-channel); the kernel is compiled -fmad=false for "
+                                 "bit-exactness, so 0.5 is its ceiling against the FMA-counted nominal peak"},
+                "slower_roof": "fp32" if fp32_ceiling < hbm_ceiling else "hbm",
+                "frac_of_slower_roof_whole_step": (audio_s / (step_ms * 1e-3)) / min(fp32_ceiling, hbm_ceiling) if world == 1 else None,
+                "entropy_kernel_ms": ent_ms, "granule_kernel_share_of_step": gran_ms / (gran_ms + ent_ms)}
+
+    # ---- end to end: MP3 bytes (host) -> PCM floats (pinned host) ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin_pcm = torch.empty(hb.pcm_floats, dtype=torch.float32).pin_memory()
+        ptr = pin_pcm.data_ptr()
+        parts = []
+
+        def e2e_step():
+            t_a = time.perf_counter()
+            prepass()                        # host prepass of every stream (its output equals `scans`)
+            t_b = time.perf_counter()
+            rb.reupload()                    # H2D: main-data blob + descriptors from pinned memory
+            rb.run()
+            rb.download_into(ptr, 0, hb.pcm_floats)   # D2H of the whole PCM result (synchronises)
+            t_c = time.perf_counter()
+            return t_b - t_a, t_c - t_b
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            parts.append(e2e_step())
+        barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        h2d = int(hb.blob.size) + hb.descs.size * 16 + hb.streams.size * 56
+        e2e = {"value": total_audio / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": pcm_bytes,
+               "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
+               "host_prepass_ms": 1e3 * float(np.mean([p[0] for p in parts])), "host_prepass_threads": threads,
+               "copy_and_kernels_ms": 1e3 * float(np.mean([p[1] for p in parts])),
+               "without_prepass_value": total_audio / max_over_ranks(float(np.mean([p[1] for p in parts]))),
+               "checksum": float(pin_pcm[:: max(1, hb.pcm_floats // 65536)].double().abs().sum())}
+        del pin_pcm
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same workload ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ht = host_threads()
+        a1, w1 = cpu_decode_throughput(streams[:1], 1)
+        per_stream = w1
+        n_sample = int(max(ht, min(len(streams), args.cpu_baseline_seconds * ht / max(per_stream, 1e-6))))
+        a, w = cpu_decode_throughput(streams[:n_sample], ht)
+        cpu = {"value": a / w, "unit": UNIT, "cores": ht, "kind": "port",
+               "sample": f"first {n_sample} of the {len(streams)} streams, {args.seconds:g} s each, transcode loop (1024-frame reads)",
+               "single_thread_value": a1 / w1,
+               "note": "C restatement of the reference's D decoder (no D compiler in this image)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args, args.streams),
+                "audio_seconds_per_step": total_audio, "granule_channels_per_gpu": n_grch,
+                "clocks": clocks, "gpu_launches": launches if nk == args.steps else int(launches * args.steps / nk),
+                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                "setup": {"generate_s": t_gen, "prepass_s": t_scan, "host_threads": threads}}
+        print(json.dumps(line), flush=True)
+    rb.free()
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

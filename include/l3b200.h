@@ -104,15 +104,19 @@ int l3b_decode_batch(l3b_ctx_t* ctx, const l3b_batch_t* batch);
  * l3b_batch_upload keeps descriptors + blob on the GPU and allocates the PCM buffer there. */
 typedef struct l3b_resident l3b_resident_t;
 int l3b_batch_upload(l3b_ctx_t* ctx, const l3b_batch_t* batch, l3b_resident_t** out);
+/* Refresh the inputs of an existing resident batch (same shape) from HOST memory: the per-step H2D of a
+ * steady-state pipeline that reuses its device buffers. */
+int l3b_batch_reupload(l3b_ctx_t* ctx, l3b_resident_t* r, const l3b_batch_t* batch);
 int l3b_batch_run(l3b_ctx_t* ctx, l3b_resident_t* r);                      /* async on the context stream */
 int l3b_batch_sync(l3b_ctx_t* ctx);
 int l3b_batch_download(l3b_ctx_t* ctx, l3b_resident_t* r, float* pcm_host, uint64_t first_float, uint64_t n_floats);
 int l3b_batch_download_taps(l3b_ctx_t* ctx, l3b_resident_t* r, const l3b_taps_t* taps);
 void* l3b_batch_device_pcm(l3b_resident_t* r);                              /* raw device pointer (for checksums/tests) */
 void l3b_batch_free(l3b_ctx_t* ctx, l3b_resident_t* r);
-/* CUDA-event timing of the most recent l3b_batch_run: total and per-kernel milliseconds
- * (ms[0] entropy kernel, ms[1] granule kernel stereo, ms[2] granule kernel mono), launches issued. */
-int l3b_batch_last_timing(l3b_ctx_t* ctx, float ms[3], int* launches);
+/* CUDA-event timing summed over the most recent `last_runs` calls of l3b_batch_run (at most 64 are kept;
+ * synchronises the context stream): ms[0] entropy kernel, ms[1] granule kernel (stereo tiles),
+ * ms[2] granule kernel (mono tiles); *launches = kernels launched in those runs. */
+int l3b_batch_timing(l3b_ctx_t* ctx, int last_runs, float ms[3], int* launches);
 void* l3b_ctx_cuda_stream(l3b_ctx_t* ctx);
 
 /* -------- layer 2: host prepass + AudioStream surface ------------------------------------------ */

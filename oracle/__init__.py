@@ -60,6 +60,9 @@ def lib():
         L.l3o_stream_read_float.restype = C.c_int
         L.l3o_stream_seek.argtypes = [C.c_void_p, C.c_int]
         L.l3o_stream_seek.restype = C.c_int
+        L.l3o_transcode_loop.restype = C.c_longlong
+        L.l3o_transcode_loop.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.l3o_set_tap.argtypes = [C.c_void_p]
         L.l3o_enable_timers.argtypes = [C.c_int]
         L.l3o_get_timers.argtypes = [C.POINTER(C.c_double * 7)]
@@ -128,3 +131,18 @@ def decode_all(data: bytes, chunk_frames: int = 1024, taps: int = 0):
     if taps:
         return pcm, tap_arr[:min(tap.count, taps)]
     return pcm, None
+
+
+def transcode_loop(data: bytes, chunk_frames: int = 1024, keep: bool = False):
+    """Whole decode inside C (GIL released): returns (frames, channels, hz, pcm or None)."""
+    L = lib()
+    nch, hz = C.c_int(), C.c_int()
+    if keep:
+        probe = OracleStream(data)
+        cap = int(probe.length_frames) * probe.channels + 2304 * 4
+        probe.close()
+        out = np.empty(cap, np.float32)
+        n = L.l3o_transcode_loop(data, len(data), chunk_frames, out.ctypes.data, cap, C.byref(nch), C.byref(hz))
+        return n, nch.value, hz.value, out[: max(n, 0) * max(nch.value, 1)].reshape(-1, max(nch.value, 1))
+    n = L.l3o_transcode_loop(data, len(data), chunk_frames, None, 0, C.byref(nch), C.byref(hz))
+    return n, nch.value, hz.value, None

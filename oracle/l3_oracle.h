@@ -132,6 +132,9 @@ int l3o_stream_read_float(l3o_stream_t* s, float* out, int frames);      /* stre
 int l3o_stream_seek(l3o_stream_t* s, int frame);                         /* stream.d:1100-1107: 1 = ok, 0 = refused */
 int l3o_stream_tell(const l3o_stream_t* s);                              /* stream.d:1214-1218 */
 int l3o_stream_last_error(const l3o_stream_t* s);
+/* examples/transcode/source/main.d:52-78 loop shape; see l3_oracle_ex.c */
+long long l3o_transcode_loop(const uint8_t* data, size_t size, int chunk_frames, float* out, size_t cap_samples,
+                             int* channels_out, int* hz_out);
 
 #ifdef __cplusplus
 }

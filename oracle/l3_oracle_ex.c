@@ -494,3 +494,34 @@ int l3o_stream_seek(l3o_stream_t* s, int frame)
 
 int l3o_stream_tell(const l3o_stream_t* s) { return (int)s->ex.cur_sample / s->channels; }
 int l3o_stream_last_error(const l3o_stream_t* s) { return s->ex.last_error; }
+
+/* The transcode example's driver loop (examples/transcode/source/main.d:52-78): open, then read
+ * `chunk_frames`-frame chunks until a read returns 0.  With out == NULL the chunk buffer is reused,
+ * exactly like the example; otherwise the PCM is appended to out (cap_samples interleaved samples).
+ * Returns the number of frames decoded, or -1 when the data is not detected as MP3. */
+long long l3o_transcode_loop(const uint8_t* data, size_t size, int chunk_frames, float* out, size_t cap_samples,
+                             int* channels_out, int* hz_out)
+{
+    l3o_stream_t* s = l3o_stream_open_memory(data, size);
+    if (!s) return -1;
+    int nch = s->channels;
+    if (channels_out) *channels_out = nch;
+    if (hz_out) *hz_out = s->samplerate;
+    float* chunk = (float*)malloc(sizeof(float) * (size_t)chunk_frames * (size_t)nch);
+    long long total = 0;
+    size_t at = 0;
+    for (;;) {
+        int n = l3o_stream_read_float(s, chunk, chunk_frames);
+        if (n <= 0) break;
+        if (out) {
+            size_t cnt = (size_t)n * (size_t)nch;
+            if (at + cnt > cap_samples) cnt = cap_samples - at;
+            memcpy(out + at, chunk, cnt * sizeof(float));
+            at += cnt;
+        }
+        total += n;
+    }
+    free(chunk);
+    l3o_stream_close(s);
+    return total;
+}
