@@ -299,6 +299,53 @@ __global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
 // =====================================================================================================
 // Granule kernel
 // =====================================================================================================
+//
+// One warp decodes a run of consecutive granules of one stream.  For stereo streams the two channels
+// travel together in every register as a float2 (T = float2): additions use the packed FADD2 of sm_100,
+// multiplications stay scalar FMULs.  (ptxas 12.9 contracts FMUL2 -> FADD2 into FFMA2 even under
+// -fmad=false; scalar multiplies feeding packed adds are left alone, which keeps every value rounded
+// exactly like the un-fused reference.)  Stage mapping inside the warp:
+//   requant + MS stereo     lane = coefficient pair (9 per lane)
+//   antialias + IMDCT       lane = subband (overlap of the previous granule lives in registers)
+//   DCT-32                  lane = time slot (18 lanes)
+//   window                  lane = (slot parity, inner index i of minimp3.d:1371), 16-tap sliding register window
+// Shared memory per warp: spectrum T[608], DCT history T[33 rows x 33], small tables.  No block barriers.
+
+template <int NCH> struct VT;
+template <> struct VT<1> {
+    typedef float T;
+    static __device__ __forceinline__ T zero() { return 0.0f; }
+    static __device__ __forceinline__ T add(T a, T b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ T sub(T a, T b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ T mul(T a, T b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ T muls(T a, float s) { return __fmul_rn(a, s); }
+    static __device__ __forceinline__ T mulw(T a, float w0, float) { return __fmul_rn(a, w0); }
+    static __device__ __forceinline__ T neg(T a) { return -a; }
+    static __device__ __forceinline__ T shfl_up(T a) { return __shfl_up_sync(0xffffffffu, a, 1); }
+    static __device__ __forceinline__ T shfl_down(T a) { return __shfl_down_sync(0xffffffffu, a, 1); }
+    static __device__ __forceinline__ T sel(bool c0, bool, T a, T b) { return c0 ? a : b; }
+    static __device__ __forceinline__ float ch(T a, int) { return a; }
+    static __device__ __forceinline__ T pack(float a, float) { return a; }
+};
+template <> struct VT<2> {
+    typedef float2 T;
+    static __device__ __forceinline__ T zero() { return make_float2(0.0f, 0.0f); }
+    static __device__ __forceinline__ T neg(T a) { return make_float2(-a.x, -a.y); }
+    static __device__ __forceinline__ T add(T a, T b) { return __fadd2_rn(a, b); }
+    static __device__ __forceinline__ T sub(T a, T b) { return __fadd2_rn(a, neg(b)); }
+    static __device__ __forceinline__ T mul(T a, T b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+    static __device__ __forceinline__ T muls(T a, float s) { return make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s)); }
+    static __device__ __forceinline__ T mulw(T a, float w0, float w1) { return make_float2(__fmul_rn(a.x, w0), __fmul_rn(a.y, w1)); }
+    static __device__ __forceinline__ T shfl_up(T a) {
+        return make_float2(__shfl_up_sync(0xffffffffu, a.x, 1), __shfl_up_sync(0xffffffffu, a.y, 1));
+    }
+    static __device__ __forceinline__ T shfl_down(T a) {
+        return make_float2(__shfl_down_sync(0xffffffffu, a.x, 1), __shfl_down_sync(0xffffffffu, a.y, 1));
+    }
+    static __device__ __forceinline__ T sel(bool c0, bool c1, T a, T b) { return make_float2(c0 ? a.x : b.x, c1 ? a.y : b.y); }
+    static __device__ __forceinline__ float ch(T a, int c) { return c ? a.y : a.x; }
+    static __device__ __forceinline__ T pack(float a, float b) { return make_float2(a, b); }
+};
 
 // L3_ldexp_q2 (minimp3.d:646-657): y * 2^(-exp_q2/4) by repeated multiplication, same rounding steps.
 __device__ __forceinline__ float ldexp_q2(float y, int exp_q2) {
@@ -322,153 +369,219 @@ __device__ __noinline__ float pow43_big(const float* pow43, int x) {
 __device__ __forceinline__ float requant(const float* pow43, int v, float s) {
     int a = v < 0 ? -v : v;
     float pw = a < 129 ? pow43[a] : pow43_big(pow43, a);
-    float r = pw * s;
+    float r = __fmul_rn(pw, s);
     return v < 0 ? -r : r;
 }
 
 // L3_dct3_9 (minimp3.d:1022-1060), in registers
-__device__ __forceinline__ void dct3_9(float* y) {
-    float s0, s1, s2, s3, s4, s5, s6, s7, s8, t0, t2, t4;
+template <int NCH>
+__device__ __forceinline__ void dct3_9(typename VT<NCH>::T* y) {
+    typedef VT<NCH> V;
+    typedef typename V::T T;
+    T s0, s1, s2, s3, s4, s5, s6, s7, s8, t0, t2, t4;
     s0 = y[0]; s2 = y[2]; s4 = y[4]; s6 = y[6]; s8 = y[8];
-    t0 = s0 + s6 * 0.5f;
-    s0 -= s6;
-    t4 = (s4 + s2) * 0.93969262f;
-    t2 = (s8 + s2) * 0.76604444f;
-    s6 = (s4 - s8) * 0.17364818f;
-    s4 += s8 - s2;
+    t0 = V::add(s0, V::muls(s6, 0.5f));
+    s0 = V::sub(s0, s6);
+    t4 = V::muls(V::add(s4, s2), 0.93969262f);
+    t2 = V::muls(V::add(s8, s2), 0.76604444f);
+    s6 = V::muls(V::sub(s4, s8), 0.17364818f);
+    s4 = V::add(s4, V::sub(s8, s2));
 
-    s2 = s0 - s4 * 0.5f;
-    y[4] = s4 + s0;
-    s8 = t0 - t2 + s6;
-    s0 = t0 - t4 + t2;
-    s4 = t0 + t4 - s6;
+    s2 = V::sub(s0, V::muls(s4, 0.5f));
+    y[4] = V::add(s4, s0);
+    s8 = V::add(V::sub(t0, t2), s6);
+    s0 = V::add(V::sub(t0, t4), t2);
+    s4 = V::sub(V::add(t0, t4), s6);
 
     s1 = y[1]; s3 = y[3]; s5 = y[5]; s7 = y[7];
 
-    s3 *= 0.86602540f;
-    t0 = (s5 + s1) * 0.98480775f;
-    t4 = (s5 - s7) * 0.34202014f;
-    t2 = (s1 + s7) * 0.64278761f;
-    s1 = (s1 - s5 - s7) * 0.86602540f;
+    s3 = V::muls(s3, 0.86602540f);
+    t0 = V::muls(V::add(s5, s1), 0.98480775f);
+    t4 = V::muls(V::sub(s5, s7), 0.34202014f);
+    t2 = V::muls(V::add(s1, s7), 0.64278761f);
+    s1 = V::muls(V::sub(V::sub(s1, s5), s7), 0.86602540f);
 
-    s5 = t0 - s3 - t2;
-    s7 = t4 - s3 - t0;
-    s3 = t4 + s3 - t2;
+    s5 = V::sub(V::sub(t0, s3), t2);
+    s7 = V::sub(V::sub(t4, s3), t0);
+    s3 = V::sub(V::add(t4, s3), t2);
 
-    y[0] = s4 - s7;
-    y[1] = s2 + s1;
-    y[2] = s0 - s3;
-    y[3] = s8 + s5;
-    y[5] = s8 - s5;
-    y[6] = s0 + s3;
-    y[7] = s2 - s1;
-    y[8] = s4 + s7;
+    y[0] = V::sub(s4, s7);
+    y[1] = V::add(s2, s1);
+    y[2] = V::sub(s0, s3);
+    y[3] = V::add(s8, s5);
+    y[5] = V::sub(s8, s5);
+    y[6] = V::add(s0, s3);
+    y[7] = V::sub(s2, s1);
+    y[8] = V::add(s4, s7);
 }
 
-// L3_imdct36 for one band (minimp3.d:1062-1100): x -> out, overlap updated in place
-__device__ __forceinline__ void imdct36_band(const float* x, float* ovl, int wsel, float* out) {
-    float co[9], si[9];
-    co[0] = -x[0];
+// L3_imdct36 for one band (minimp3.d:1062-1100).  ws0/ws1: window row (0 normal, 1 stop) per channel.
+template <int NCH>
+__device__ __forceinline__ void imdct36_band(const typename VT<NCH>::T* x, typename VT<NCH>::T* ovl, int ws0, int ws1,
+                                             typename VT<NCH>::T* out) {
+    typedef VT<NCH> V;
+    typedef typename V::T T;
+    T co[9], si[9];
+    co[0] = V::neg(x[0]);
     si[0] = x[17];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        si[8 - 2 * i] = x[4 * i + 1] - x[4 * i + 2];
-        co[1 + 2 * i] = x[4 * i + 1] + x[4 * i + 2];
-        si[7 - 2 * i] = x[4 * i + 4] - x[4 * i + 3];
-        co[2 + 2 * i] = -(x[4 * i + 3] + x[4 * i + 4]);
+        si[8 - 2 * i] = V::sub(x[4 * i + 1], x[4 * i + 2]);
+        co[1 + 2 * i] = V::add(x[4 * i + 1], x[4 * i + 2]);
+        si[7 - 2 * i] = V::sub(x[4 * i + 4], x[4 * i + 3]);
+        co[2 + 2 * i] = V::neg(V::add(x[4 * i + 3], x[4 * i + 4]));
     }
-    dct3_9(co);
-    dct3_9(si);
-    si[1] = -si[1];
-    si[3] = -si[3];
-    si[5] = -si[5];
-    si[7] = -si[7];
-    const float* window = c_mdctw + 18 * wsel;
+    dct3_9<NCH>(co);
+    dct3_9<NCH>(si);
+    si[1] = V::neg(si[1]);
+    si[3] = V::neg(si[3]);
+    si[5] = V::neg(si[5]);
+    si[7] = V::neg(si[7]);
+    const float* wa = c_mdctw + 18 * ws0;
+    const float* wb = c_mdctw + 18 * ws1;
 #pragma unroll
     for (int i = 0; i < 9; i++) {
-        float o = ovl[i];
-        float sum = co[i] * c_twid9[9 + i] + si[i] * c_twid9[0 + i];
-        ovl[i] = co[i] * c_twid9[0 + i] - si[i] * c_twid9[9 + i];
-        out[i] = o * window[0 + i] - sum * window[9 + i];
-        out[17 - i] = o * window[9 + i] + sum * window[0 + i];
+        T o = ovl[i];
+        T sum = V::add(V::muls(co[i], c_twid9[9 + i]), V::muls(si[i], c_twid9[0 + i]));
+        ovl[i] = V::sub(V::muls(co[i], c_twid9[0 + i]), V::muls(si[i], c_twid9[9 + i]));
+        out[i] = V::sub(V::mulw(o, wa[0 + i], wb[0 + i]), V::mulw(sum, wa[9 + i], wb[9 + i]));
+        out[17 - i] = V::add(V::mulw(o, wa[9 + i], wb[9 + i]), V::mulw(sum, wa[0 + i], wb[0 + i]));
     }
 }
 
 // L3_idct3 / L3_imdct12 (minimp3.d:1102-1129); X(k) = x[OFF + 3k]
-template <int OFF>
-__device__ __forceinline__ void imdct12(const float* x, float* dst, float* overlap) {
-    float co[3], si[3];
+template <int NCH, int OFF>
+__device__ __forceinline__ void imdct12(const typename VT<NCH>::T* x, typename VT<NCH>::T* dst, typename VT<NCH>::T* overlap) {
+    typedef VT<NCH> V;
+    typedef typename V::T T;
+    T co[3], si[3];
     {
-        float x0 = -x[OFF + 0], x1 = x[OFF + 6] + x[OFF + 3], x2 = x[OFF + 12] + x[OFF + 9];
-        float m1 = x1 * 0.86602540f, a1 = x0 - x2 * 0.5f;
-        co[1] = x0 + x2; co[0] = a1 + m1; co[2] = a1 - m1;
+        T x0 = V::neg(x[OFF + 0]), x1 = V::add(x[OFF + 6], x[OFF + 3]), x2 = V::add(x[OFF + 12], x[OFF + 9]);
+        T m1 = V::muls(x1, 0.86602540f), a1 = V::sub(x0, V::muls(x2, 0.5f));
+        co[1] = V::add(x0, x2); co[0] = V::add(a1, m1); co[2] = V::sub(a1, m1);
     }
     {
-        float x0 = x[OFF + 15], x1 = x[OFF + 12] - x[OFF + 9], x2 = x[OFF + 6] - x[OFF + 3];
-        float m1 = x1 * 0.86602540f, a1 = x0 - x2 * 0.5f;
-        si[1] = x0 + x2; si[0] = a1 + m1; si[2] = a1 - m1;
+        T x0 = x[OFF + 15], x1 = V::sub(x[OFF + 12], x[OFF + 9]), x2 = V::sub(x[OFF + 6], x[OFF + 3]);
+        T m1 = V::muls(x1, 0.86602540f), a1 = V::sub(x0, V::muls(x2, 0.5f));
+        si[1] = V::add(x0, x2); si[0] = V::add(a1, m1); si[2] = V::sub(a1, m1);
     }
-    si[1] = -si[1];
+    si[1] = V::neg(si[1]);
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        float o = overlap[i];
-        float sum = co[i] * c_twid3[3 + i] + si[i] * c_twid3[0 + i];
-        overlap[i] = co[i] * c_twid3[0 + i] - si[i] * c_twid3[3 + i];
-        dst[i] = o * c_twid3[2 - i] - sum * c_twid3[5 - i];
-        dst[5 - i] = o * c_twid3[5 - i] + sum * c_twid3[2 - i];
+        T o = overlap[i];
+        T sum = V::add(V::muls(co[i], c_twid3[3 + i]), V::muls(si[i], c_twid3[0 + i]));
+        overlap[i] = V::sub(V::muls(co[i], c_twid3[0 + i]), V::muls(si[i], c_twid3[3 + i]));
+        dst[i] = V::sub(V::muls(o, c_twid3[2 - i]), V::muls(sum, c_twid3[5 - i]));
+        dst[5 - i] = V::add(V::muls(o, c_twid3[5 - i]), V::muls(sum, c_twid3[2 - i]));
     }
 }
 
 // L3_imdct_short for one band (minimp3.d:1131-1142)
-__device__ __forceinline__ void imdct_short_band(const float* x, float* ovl, float* out) {
+template <int NCH>
+__device__ __forceinline__ void imdct_short_band(const typename VT<NCH>::T* x, typename VT<NCH>::T* ovl, typename VT<NCH>::T* out) {
+    typedef typename VT<NCH>::T T;
 #pragma unroll
     for (int i = 0; i < 6; i++) out[i] = ovl[i];
-    imdct12<0>(x, out + 6, ovl + 6);
-    imdct12<1>(x, out + 12, ovl + 6);
-    float nd[6];
-    imdct12<2>(x, nd, ovl + 6);
+    imdct12<NCH, 0>(x, out + 6, ovl + 6);
+    imdct12<NCH, 1>(x, out + 12, ovl + 6);
+    T nd[6];
+    imdct12<NCH, 2>(x, nd, ovl + 6);
 #pragma unroll
     for (int i = 0; i < 6; i++) ovl[i] = nd[i];
 }
 
-// address of history row for absolute slot tt (>= 0) of one channel: parity array tt&1, row (tt>>1) mod 18
-__device__ __forceinline__ const float* drow(const float* Dch, int tt) {
-    int r = tt >> 1;
-    r = r >= 36 ? r - 36 : (r >= 18 ? r - 18 : r);
-    return Dch + (tt & 1) * kDParity + r * 33;
+constexpr int kDRows = 33;    // 15 history rows + 18 rows of the current granule
+constexpr int kDStride = 33;  // T elements per row (odd: the DCT's per-slot column writes hit distinct banks)
+constexpr int kMaxIter = kTileGranules + 2;
+
+// ---- mbarrier + TMA (1-D bulk copy) helpers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// per-warp shared memory
 template <int NCH>
-__global__ void __launch_bounds__(32 * NCH) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
-    __shared__ __align__(16) float s_xr[NCH][kXrStride];
-    __shared__ __align__(16) float s_D[NCH][2 * kDParity];
-    __shared__ float s_scf[NCH][40];
-    __shared__ float s_pow43[132];
-    __shared__ uint8_t s_sfbpair[3][288];
-    __shared__ uint8_t s_sfbw[3][40];
-    __shared__ uint16_t s_sfbo[3][40];
-    __shared__ uint8_t s_ist[40];
-    __shared__ uint8_t s_smode[40];
-    __shared__ float s_kl[40], s_kr[40];
-    __shared__ int s_maxband[3];
+struct __align__(16) WarpSmem {
+    typename VT<NCH>::T xr[kXrStride];         // spectrum (natural layout) / IMDCT output (x19 padded layout)
+    typename VT<NCH>::T D[kDRows * kDStride];  // DCT-32 outputs: rows 0..14 history, 15..32 this granule
+    uint4 st_is[NCH * kIsChunks];              // TMA-staged inputs of the next granule: quantised spectra,
+    uint4 st_rec[NCH * kSfRecBytes / 16];      //   scalefactor records,
+    uint4 st_desc[NCH];                        //   descriptors
+    float scf[NCH][40];
+    uint8_t sfbpair[3][288];
+    uint8_t ist[40];
+    uint8_t smode[40];
+    float kl[40], kr[40];
+    uint64_t mbar;
+};
 
-    if (blockIdx.x >= n_tiles) return;
-    const Tile T = tiles[blockIdx.x];
-    const l3b_stream_desc_t S = p.streams[T.stream];
-    const int tid = threadIdx.x, nthr = 32 * NCH;
-    const int ch = tid >> 5, lane = tid & 31;
+// The (rare) band where the two channels of a granule use different transforms: one channel at a time.
+__device__ __noinline__ void imdct_split(float2* x, float2* ovl, float2* y, bool sh0, bool sh1, int bt0, int bt1) {
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        float xs[18], os[9], ys[18];
+#pragma unroll
+        for (int i = 0; i < 18; i++) xs[i] = c ? x[i].y : x[i].x;
+#pragma unroll
+        for (int i = 0; i < 9; i++) os[i] = c ? ovl[i].y : ovl[i].x;
+        if (c ? sh1 : sh0) imdct_short_band<1>(xs, os, ys);
+        else imdct36_band<1>(xs, os, (c ? bt1 : bt0) == 3 ? 1 : 0, 0, ys);
+#pragma unroll
+        for (int i = 0; i < 18; i++) { if (c) y[i].y = ys[i]; else y[i].x = ys[i]; }
+#pragma unroll
+        for (int i = 0; i < 9; i++) { if (c) ovl[i].y = os[i]; else ovl[i].x = os[i]; }
+    }
+}
+__device__ __forceinline__ void imdct_split(float*, float*, float*, bool, bool, int, int) {}
+
+template <int NCH, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
+    typedef VT<NCH> V;
+    typedef typename V::T T;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float* s_pow43 = reinterpret_cast<float*>(smem_raw);  // 132 floats, shared by the CTA
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem<NCH>& W = *reinterpret_cast<WarpSmem<NCH>*>(smem_raw + 528 + (size_t)warp * sizeof(WarpSmem<NCH>));
+
+    for (int i = threadIdx.x; i < 129; i += 32 * WARPS) s_pow43[i] = p.t.pow43[i];
+
+    const uint32_t tile_idx = blockIdx.x * WARPS + warp;
+    const bool have_tile = tile_idx < n_tiles;
+    const Tile tile = have_tile ? tiles[tile_idx] : Tile{0, 0, 0};
+    const l3b_stream_desc_t S = p.streams[tile.stream];
     const bool mpeg1 = S.mpeg1 != 0;
     const int row = S.sr_idx;
 
-    for (int i = tid; i < 129; i += nthr) s_pow43[i] = p.t.pow43[i];
-    for (int i = tid; i < 3 * 288; i += nthr) (&s_sfbpair[0][0])[i] = p.t.sfb_of_pair[row * 3 * 288 + i];
-    for (int i = tid; i < 3 * 40; i += nthr) {
-        (&s_sfbw[0][0])[i] = p.t.sfb_width[row * 120 + i];
-        (&s_sfbo[0][0])[i] = p.t.sfb_start[row * 120 + i];
-    }
-    for (int i = lane; i < 2 * kDParity; i += 32) s_D[ch][i] = 0.0f;
+    for (int i = lane; i < 3 * 288 / 4; i += 32)
+        reinterpret_cast<uint32_t*>(&W.sfbpair[0][0])[i] = reinterpret_cast<const uint32_t*>(p.t.sfb_of_pair + row * 3 * 288)[i];
+    for (int i = lane; i < 15 * kDStride; i += 32) W.D[i] = V::zero();
+    if (lane == 0) mbar_init(&W.mbar, 1);
 
-    // synthesis window weights of this lane: inner index ii = lane & 15 (0..14 active)
+    // synthesis window weights of this lane: inner index ii = lane & 15 (0..14 active), slot parity par
     const int ii = lane & 15, par = lane >> 4;
     float w0[8], w1[8];
 #pragma unroll
@@ -478,344 +591,408 @@ __global__ void __launch_bounds__(32 * NCH) l3_granule_kernel(BatchParams p, con
     }
 
     // recompute halo: up to two granules before the tile, unless decoder state was zeroed in between
-    int start = (int)T.g0;
-    for (int depth = 0; depth < 2 && start > 0; depth++) {
+    int start = (int)tile.g0;
+    for (int depth = 0; depth < 2 && start > 0 && have_tile; depth++) {
         const l3b_grch_desc_t* dp = p.grch + S.first_grch + (uint64_t)start * NCH;
         if (__ldg(&dp->w3) >> 31) break;
         start--;
     }
-    float ovl[9];
+    const int n_iter = have_tile ? (int)(tile.g0 + tile.ng) - start : 0;
+    T ovl[9];
 #pragma unroll
-    for (int i = 0; i < 9; i++) ovl[i] = 0.0f;
+    for (int i = 0; i < 9; i++) ovl[i] = V::zero();
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    const float* Dch = s_D[ch];
-    float* xr = s_xr[ch];
     const int n_long_bands_mixed = 2 << (row == 1 ? 1 : 0);  // minimp3.d:1218
-    int dgc = 0;                                             // granules that went through the DCT stage
-    const int g_end = (int)(T.g0 + T.ng);
+    const uint64_t skipf = S.pcm_skip / NCH, countf = S.pcm_count / NCH;   // in frames
+    T* const pcm = reinterpret_cast<T*>(p.pcm + S.pcm_off);
+    constexpr uint32_t kStageBytes = NCH * (kIsChunks * 16 + kSfRecBytes + 16);
 
-    for (int g = start; g < g_end; g++) {
-        const uint64_t di = S.first_grch + (uint64_t)g * NCH + ch;
-        const Desc d = load_desc(p.grch + di);
-        const int mode = g >= (int)T.g0 ? 2 : (g == (int)T.g0 - 1 ? 1 : 0);
-        if (d.reset_before() && g != start) {
+    auto prefetch = [&](int g) {  // lane 0: TMA bulk copies of granule g's inputs into the staging buffers
+        const uint64_t di = S.first_grch + (uint64_t)g * NCH;
+        mbar_expect_tx(&W.mbar, kStageBytes);
+        tma_load_1d(W.st_is, p.is + di * kIsChunks, NCH * kIsChunks * 16, &W.mbar);
+        tma_load_1d(W.st_rec, p.sf + di * kSfRecBytes, NCH * kSfRecBytes, &W.mbar);
+        tma_load_1d(W.st_desc, p.grch + di, NCH * 16, &W.mbar);
+    };
+    if (lane == 0 && n_iter > 0) prefetch(start);
+
+    for (int it = 0; it < kMaxIter; it++) {
+        const bool act = it < n_iter;
+        const int g = start + it;
+        const int mode = g >= (int)tile.g0 ? 2 : (g == (int)tile.g0 - 1 ? 1 : 0);
+        Desc d0, d1;
+        d0.bit_start = d0.w1 = d0.w2 = d0.w3 = 0;
+        d1 = d0;
+        int kind0 = 0, kind1 = 0, hb = 0;
+        bool ms_frame = false, istereo = false;
+        if (act) {
+            mbar_wait(&W.mbar, it & 1);
+            {
+                const uint4 v = W.st_desc[0];
+                d0.bit_start = v.x; d0.w1 = v.y; d0.w2 = v.z; d0.w3 = v.w;
+                const uint4 u = W.st_desc[NCH - 1];
+                d1.bit_start = u.x; d1.w1 = u.y; d1.w2 = u.z; d1.w3 = u.w;
+            }
+            if (d0.reset_before() && it != 0) {
 #pragma unroll
-            for (int i = 0; i < 9; i++) ovl[i] = 0.0f;
-            for (int i = lane; i < 2 * kDParity; i += 32) s_D[ch][i] = 0.0f;
+                for (int i = 0; i < 9; i++) ovl[i] = V::zero();
+                for (int i = lane; i < 15 * kDStride; i += 32) W.D[i] = V::zero();
+            }
+            kind0 = d0.kind(); kind1 = d1.kind();
+            hb = d0.hdr_bits();
+            ms_frame = (hb & 0xE) == 0x6;       // HDR_IS_MS_STEREO
+            istereo = NCH == 2 && (hb & 1);     // HDR_TEST_I_STEREO
+            const uint8_t* rec0 = reinterpret_cast<const uint8_t*>(W.st_rec);
+            const uint8_t* rec1 = rec0 + (NCH - 1) * kSfRecBytes;
+
+            // ---------------- band gains (minimp3.d:714-719) ----------------
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const Desc& d = c ? d1 : d0;
+                const uint8_t* rec = c ? rec1 : rec0;
+                const int kind = c ? kind1 : kind0;
+                const int n_sfb = kind == 0 ? 22 : (kind == 1 ? 39 : (mpeg1 ? 38 : 36));
+                const int gain_exp = d.global_gain() - 4 - 210 - (ms_frame ? 2 : 0);
+                const float gain = ldexp_q2(2048.0f, 44 - gain_exp);
+                const int scf_shift = d.scalefac_scale() + 1;
+                for (int i = lane; i < 40; i += 32) {
+                    float v = 0.0f;
+                    if (i < n_sfb) v = ldexp_q2(gain, (int)rec[i] << scf_shift);
+                    W.scf[c][i] = v;
+                }
+            }
+            if (istereo)
+                for (int i = lane; i < 40; i += 32) W.ist[i] = rec1[40 + i];
             __syncwarp();
-        }
-        const int kind = d.kind();
-        const int hb = d.hdr_bits();
-        const bool ms_frame = (hb & 0xE) == 0x6;                 // HDR_IS_MS_STEREO
-        const bool istereo = NCH == 2 && (hb & 1);               // HDR_TEST_I_STEREO
-        const int n_long_sfb = kind == 0 ? 22 : (kind == 1 ? 0 : (mpeg1 ? 8 : 6));
-        const int n_sfb = n_long_sfb + (kind == 0 ? 0 : (kind == 1 ? 39 : 30));
-        const uint8_t* rec = p.sf + di * kSfRecBytes;
 
-        // ---------------- band gains (minimp3.d:714-719) ----------------
-        {
-            const int gain_exp = d.global_gain() - 4 - 210 - (ms_frame ? 2 : 0);
-            const float gain = ldexp_q2(2048.0f, 44 - gain_exp);
-            const int scf_shift = d.scalefac_scale() + 1;
-            for (int i = lane; i < 40; i += 32) {
-                float v = 0.0f;
-                if (i < n_sfb) v = ldexp_q2(gain, (int)__ldg(rec + i) << scf_shift);
-                s_scf[ch][i] = v;
+            // ---------------- requantisation (minimp3.d:813-816, 846, 874-878) + MS stereo (:885-896) -------
+            {
+                const int nch0 = *reinterpret_cast<const uint16_t*>(rec0 + 80);
+                const int nch1 = *reinterpret_cast<const uint16_t*>(rec1 + 80);
+                const uint32_t* isw0 = reinterpret_cast<const uint32_t*>(W.st_is);
+                const uint32_t* isw1 = isw0 + (NCH - 1) * (kIsChunks * 4);
+                const bool ms_now = NCH == 2 && ms_frame && !istereo;
+#pragma unroll 3
+                for (int m = 0; m < 9; m++) {
+                    const int pi = lane + 32 * m;
+                    const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;   // chunks past nz_chunks were never written
+                    const float sa = W.scf[0][W.sfbpair[kind0][pi]];
+                    float a0 = requant(s_pow43, (int)(int16_t)(va & 0xFFFFu), sa);
+                    float a1 = requant(s_pow43, (int)(int16_t)(va >> 16), sa);
+                    if (NCH == 2) {
+                        const uint32_t vb = (pi >> 2) < nch1 ? isw1[pi] : 0u;
+                        const float sb = W.scf[NCH - 1][W.sfbpair[kind1][pi]];
+                        float b0 = requant(s_pow43, (int)(int16_t)(vb & 0xFFFFu), sb);
+                        float b1 = requant(s_pow43, (int)(int16_t)(vb >> 16), sb);
+                        if (ms_now) {
+                            const float l0 = __fadd_rn(a0, b0), r0 = __fsub_rn(a0, b0);
+                            const float l1 = __fadd_rn(a1, b1), r1 = __fsub_rn(a1, b1);
+                            a0 = l0; b0 = r0; a1 = l1; b1 = r1;
+                        }
+                        *reinterpret_cast<float4*>(&W.xr[2 * pi]) = make_float4(a0, b0, a1, b1);
+                    } else {
+                        *reinterpret_cast<float2*>(&W.xr[2 * pi]) = make_float2(a0, a1);
+                    }
+                }
             }
-            if (NCH == 2 && ch == 1 && istereo)
-                for (int i = lane; i < 40; i += 32) s_ist[i] = __ldg(rec + 40 + i);
-        }
-        __syncwarp();
-
-        // ---------------- requantisation (minimp3.d:813-816, 846, 874-878) ----------------
-        {
-            const int nchunks = *reinterpret_cast<const uint16_t*>(rec + 80);
-            const uint32_t* isw = reinterpret_cast<const uint32_t*>(p.is + di * kIsChunks);
-#pragma unroll
-            for (int m = 0; m < 9; m++) {
-                const int pi = lane + 32 * m;
-                uint32_t v = (pi >> 2) < nchunks ? __ldg(isw + pi) : 0u;
-                const float s = s_scf[ch][s_sfbpair[kind][pi]];
-                const int v0 = (int)(int16_t)(v & 0xFFFFu), v1 = (int)(int16_t)(v >> 16);
-                float2 o;
-                o.x = requant(s_pow43, v0, s);
-                o.y = requant(s_pow43, v1, s);
-                *reinterpret_cast<float2*>(xr + 2 * pi) = o;
+            __syncwarp();
+            // the staging buffers are free again: fetch the next granule while this one is transformed
+            if (lane == 0 && it + 1 < n_iter) {
+                fence_proxy_async();
+                prefetch(g + 1);
             }
-        }
 
-        // ---------------- stereo (minimp3.d:885-982, 1207-1213) ----------------
-        if (NCH == 2) {
-            __syncthreads();
-            float* L = s_xr[0];
-            float* R = s_xr[1];
-            if (istereo) {
-                // L3_intensity_stereo works on channel 0's band layout (gr_info of ch 0, minimp3.d:1209) and on
-                // channel 1's scalefac_compress (gr[1], minimp3.d:981)
-                const Desc d0 = load_desc(p.grch + S.first_grch + (uint64_t)g * NCH + 0);
-                const Desc d1 = load_desc(p.grch + S.first_grch + (uint64_t)g * NCH + 1);
-                const int kind0 = d0.kind();
+            // ---------------- intensity stereo (minimp3.d:898-982), on channel 0's band layout ----------------
+            if (NCH == 2 && istereo) {
+                float2* X = reinterpret_cast<float2*>(W.xr);
                 const int n_long_sfb0 = kind0 == 0 ? 22 : (kind0 == 1 ? 0 : (mpeg1 ? 8 : 6));
                 const int n_sfb0 = n_long_sfb0 + (kind0 == 0 ? 0 : (kind0 == 1 ? 39 : 30));
-                if (ch == 0) {
-                    // L3_stereo_top_band: last sfb (per window) of the right channel holding a non-zero value
-                    int mb0 = -1, mb1 = -1, mb2 = -1;
-                    for (int i = lane; i < n_sfb0; i += 32) {
-                        const int off = s_sfbo[kind0][i], wdt = s_sfbw[kind0][i];
-                        bool nz = false;
-                        for (int k = 0; k < wdt; k++) nz |= (R[off + k] != 0.0f);
-                        if (nz) { int c = i % 3; if (c == 0) mb0 = max(mb0, i); else if (c == 1) mb1 = max(mb1, i); else mb2 = max(mb2, i); }
-                    }
+                const uint8_t* sfbw = p.t.sfb_width + (row * 3 + kind0) * 40;
+                const uint16_t* sfbo = p.t.sfb_start + (row * 3 + kind0) * 40;
+                int mb0 = -1, mb1 = -1, mb2 = -1;
+                for (int i = lane; i < n_sfb0; i += 32) {  // L3_stereo_top_band
+                    const int off = __ldg(sfbo + i), wdt = __ldg(sfbw + i);
+                    bool nz = false;
+                    for (int k = 0; k < wdt; k++) nz |= (X[off + k].y != 0.0f);
+                    if (nz) { int c = i % 3; if (c == 0) mb0 = max(mb0, i); else if (c == 1) mb1 = max(mb1, i); else mb2 = max(mb2, i); }
+                }
 #pragma unroll
-                    for (int sft = 16; sft > 0; sft >>= 1) {
-                        mb0 = max(mb0, __shfl_xor_sync(0xffffffffu, mb0, sft));
-                        mb1 = max(mb1, __shfl_xor_sync(0xffffffffu, mb1, sft));
-                        mb2 = max(mb2, __shfl_xor_sync(0xffffffffu, mb2, sft));
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    mb0 = max(mb0, __shfl_xor_sync(0xffffffffu, mb0, sft));
+                    mb1 = max(mb1, __shfl_xor_sync(0xffffffffu, mb1, sft));
+                    mb2 = max(mb2, __shfl_xor_sync(0xffffffffu, mb2, sft));
+                }
+                if (n_long_sfb0) mb0 = mb1 = mb2 = max(max(mb0, mb1), mb2);
+                if (lane == 0) {
+                    const int max_blocks = kind0 == 0 ? 1 : 3;
+                    const int default_pos = mpeg1 ? 3 : 0;
+                    const int mb[3] = {mb0, mb1, mb2};
+                    for (int i = 0; i < max_blocks; i++) {
+                        int itop = n_sfb0 - max_blocks + i, prev = itop - max_blocks;
+                        W.ist[itop] = (uint8_t)(mb[i] >= prev ? default_pos : W.ist[prev]);
                     }
-                    if (n_long_sfb0) mb0 = mb1 = mb2 = max(max(mb0, mb1), mb2);
-                    if (lane == 0) {
-                        const int max_blocks = kind0 == 0 ? 1 : 3;
-                        const int default_pos = mpeg1 ? 3 : 0;
-                        const int mb[3] = {mb0, mb1, mb2};
-                        for (int i = 0; i < max_blocks; i++) {
-                            int itop = n_sfb0 - max_blocks + i, prev = itop - max_blocks;
-                            s_ist[itop] = (uint8_t)(mb[i] >= prev ? default_pos : s_ist[prev]);
+                }
+                __syncwarp();
+                const unsigned max_pos = mpeg1 ? 7u : 64u;
+                const int mpeg2_sh = d1.scalefac_compress() & 1;
+                for (int i = lane; i < n_sfb0; i += 32) {  // L3_stereo_process: per-sfb decision and gains
+                    const unsigned ipos = W.ist[i];
+                    const int mbc = (i % 3) == 0 ? mb0 : ((i % 3) == 1 ? mb1 : mb2);
+                    uint8_t md = 0;
+                    if (i > mbc && ipos < max_pos) {
+                        float kl, kr, s = (hb & 2) ? 1.41421356f : 1.0f;
+                        if (mpeg1) {
+                            kl = c_pan[2 * ipos];
+                            kr = c_pan[2 * ipos + 1];
+                        } else {
+                            kl = 1.0f;
+                            kr = ldexp_q2(1.0f, (int)((ipos + 1) >> 1 << mpeg2_sh));
+                            if (ipos & 1) { kl = kr; kr = 1.0f; }
                         }
-                        s_maxband[0] = mb0; s_maxband[1] = mb1; s_maxband[2] = mb2;
+                        W.kl[i] = kl * s;
+                        W.kr[i] = kr * s;
+                        md = 1;
+                    } else if (hb & 2) {
+                        md = 2;
                     }
-                    __syncwarp();
-                    // L3_stereo_process: per-sfb decision and gains
-                    const unsigned max_pos = mpeg1 ? 7u : 64u;
-                    const int mpeg2_sh = d1.scalefac_compress() & 1;
-                    for (int i = lane; i < n_sfb0; i += 32) {
-                        const unsigned ipos = s_ist[i];
-                        uint8_t md = 0;
-                        if (i > s_maxband[i % 3] && ipos < max_pos) {
-                            float kl, kr, s = (hb & 2) ? 1.41421356f : 1.0f;
-                            if (mpeg1) {
-                                kl = c_pan[2 * ipos];
-                                kr = c_pan[2 * ipos + 1];
-                            } else {
-                                kl = 1.0f;
-                                kr = ldexp_q2(1.0f, (int)((ipos + 1) >> 1 << mpeg2_sh));
-                                if (ipos & 1) { kl = kr; kr = 1.0f; }
-                            }
-                            s_kl[i] = kl * s;
-                            s_kr[i] = kr * s;
-                            md = 1;
-                        } else if (hb & 2) {
-                            md = 2;
-                        }
-                        s_smode[i] = md;
-                    }
+                    W.smode[i] = md;
                 }
-                __syncthreads();
-#pragma unroll
-                for (int m = 0; m < 9; m++) {
-                    const int k = ch * 288 + lane + 32 * m;
-                    const int sfb = s_sfbpair[kind0][k >> 1];
-                    const int md = s_smode[sfb];
-                    const float a = L[k], b = R[k];
-                    if (md == 1) { R[k] = a * s_kr[sfb]; L[k] = a * s_kl[sfb]; }
-                    else if (md == 2) { L[k] = a + b; R[k] = a - b; }
+                __syncwarp();
+                for (int m = 0; m < 18; m++) {
+                    const int k = lane + 32 * m;
+                    const int sfb = W.sfbpair[kind0][k >> 1];
+                    const int md = W.smode[sfb];
+                    const float2 v = X[k];
+                    if (md == 1) X[k] = make_float2(__fmul_rn(v.x, W.kl[sfb]), __fmul_rn(v.x, W.kr[sfb]));
+                    else if (md == 2) X[k] = make_float2(__fadd_rn(v.x, v.y), __fsub_rn(v.x, v.y));
                 }
-            } else if (ms_frame) {
-#pragma unroll
-                for (int m = 0; m < 9; m++) {
-                    const int k = ch * 288 + lane + 32 * m;
-                    const float a = L[k], b = R[k];
-                    L[k] = a + b;
-                    R[k] = a - b;
-                }
+                __syncwarp();
             }
-            __syncthreads();
-        } else {
-            __syncwarp();
         }
+        __syncthreads();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
 
         // ---------------- reorder + antialias + IMDCT + frequency inversion (minimp3.d:1215-1229) ----------
-        {
-            float x[18], y[18];
-            const int nlb = kind == 2 ? n_long_bands_mixed : 0;
-            if (kind == 0) {
+        if (act) {
+            T x[18], y[18];
+            const int bt0 = d0.block_type(), bt1 = d1.block_type();
+            const int nlb0 = kind0 == 2 ? n_long_bands_mixed : 0, nlb1 = kind1 == 2 ? n_long_bands_mixed : 0;
+            if (kind0 == 0 && kind1 == 0) {
 #pragma unroll
-                for (int i = 0; i < 18; i++) x[i] = xr[lane * 18 + i];
+                for (int i = 0; i < 18; i++) x[i] = W.xr[lane * 18 + i];
             } else {
-                const uint16_t* pm = p.t.perm + (row * 2 + (kind == 2 ? 1 : 0)) * 576 + lane * 18;
+                // short / mixed blocks: L3_reorder folded into the load through the permutation table
+                const uint16_t* pm0 = p.t.perm + (row * 2 + (kind0 == 2 ? 1 : 0)) * 576 + lane * 18;
+                const uint16_t* pm1 = p.t.perm + (row * 2 + (kind1 == 2 ? 1 : 0)) * 576 + lane * 18;
+                const float* xf = reinterpret_cast<const float*>(W.xr);
 #pragma unroll
-                for (int i = 0; i < 18; i++) x[i] = xr[__ldg(pm + i)];
+                for (int i = 0; i < 18; i++) {
+                    const int i0 = kind0 == 0 ? lane * 18 + i : (int)__ldg(pm0 + i);
+                    if (NCH == 2) {
+                        const int i1 = kind1 == 0 ? lane * 18 + i : (int)__ldg(pm1 + i);
+                        x[i] = V::pack(xf[2 * i0], xf[2 * i1 + 1]);
+                    } else {
+                        x[i] = V::pack(xf[i0], 0.0f);
+                    }
+                }
             }
-            const int aa_bands = kind == 0 ? 31 : nlb - 1;
-            if (aa_bands > 0) {
-                const bool lower = lane >= 1 && lane - 1 < aa_bands;
-                const bool upper = lane < aa_bands;
-                float nlo[8], nhi[8];
+            const int aa0 = kind0 == 0 ? 31 : nlb0 - 1, aa1 = kind1 == 0 ? 31 : nlb1 - 1;
+            if (aa0 > 0 || aa1 > 0) {
+                const bool lo0 = lane >= 1 && lane - 1 < aa0, up0 = lane < aa0;
+                const bool lo1 = lane >= 1 && lane - 1 < aa1, up1 = lane < aa1;
+                T nlo[8], nhi[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const float dn = __shfl_up_sync(0xffffffffu, x[17 - i], 1);   // band-1, element 17-i
-                    const float up = __shfl_down_sync(0xffffffffu, x[i], 1);      // band+1, element i
-                    nlo[i] = x[i] * c_aa[i] - dn * c_aa[8 + i];
-                    nhi[i] = up * c_aa[8 + i] + x[17 - i] * c_aa[i];
+                    const T dn = V::shfl_up(x[17 - i]);   // band-1, element 17-i
+                    const T up = V::shfl_down(x[i]);      // band+1, element i
+                    nlo[i] = V::sub(V::muls(x[i], c_aa[i]), V::muls(dn, c_aa[8 + i]));
+                    nhi[i] = V::add(V::muls(up, c_aa[8 + i]), V::muls(x[17 - i], c_aa[i]));
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    if (lower) x[i] = nlo[i];
-                    if (upper) x[17 - i] = nhi[i];
+                    x[i] = V::sel(lo0, lo1, nlo[i], x[i]);
+                    x[17 - i] = V::sel(up0, up1, nhi[i], x[17 - i]);
                 }
             }
-            if (d.block_type() == 2 && lane >= nlb) imdct_short_band(x, ovl, y);
-            else imdct36_band(x, ovl, (d.block_type() == 3) ? 1 : 0, y);
+            const bool sh0 = bt0 == 2 && lane >= nlb0, sh1 = bt1 == 2 && lane >= nlb1;
+            if (NCH == 1 || sh0 == sh1) {
+                if (sh0) imdct_short_band<NCH>(x, ovl, y);
+                else imdct36_band<NCH>(x, ovl, bt0 == 3 ? 1 : 0, bt1 == 3 ? 1 : 0, y);
+            } else {
+                imdct_split(x, ovl, y, sh0, sh1, bt0, bt1);
+            }
+            __syncwarp();  // every lane has consumed its inputs; the buffer is reused in the padded (x19) layout
             if (mode >= 1) {
                 if (lane & 1) {
 #pragma unroll
-                    for (int i = 1; i < 18; i += 2) y[i] = -y[i];
+                    for (int i = 1; i < 18; i += 2) y[i] = V::neg(y[i]);
                 }
-                __syncwarp();  // every lane has consumed its inputs; the buffer is reused in the padded layout
 #pragma unroll
-                for (int i = 0; i < 18; i++) xr[lane * 19 + i] = y[i];
+                for (int i = 0; i < 18; i++) W.xr[lane * 19 + i] = y[i];
             }
         }
-        if (mode == 0) { __syncwarp(); continue; }
-        __syncwarp();
+        __syncthreads();
 
         // ---------------- DCT-32 matrixing across bands, one time slot per lane (minimp3.d:1232-1298) -------
-        const int hbase = 18 * (dgc & 1) + 36;  // absolute slot of this granule's slot 0 in the 36-slot ring (+36)
-        if (lane < 18) {
-            float t[4][8];
+        if (act && mode >= 1 && lane < 18) {
+            T t[4][8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                float x0 = xr[i * 19 + lane];
-                float x1 = xr[(15 - i) * 19 + lane];
-                float x2 = xr[(16 + i) * 19 + lane];
-                float x3 = xr[(31 - i) * 19 + lane];
-                float t0 = x0 + x3;
-                float t1 = x1 + x2;
-                float t2 = (x1 - x2) * c_sec[3 * i + 0];
-                float t3 = (x0 - x3) * c_sec[3 * i + 1];
-                t[0][i] = t0 + t1;
-                t[1][i] = (t0 - t1) * c_sec[3 * i + 2];
-                t[2][i] = t3 + t2;
-                t[3][i] = (t3 - t2) * c_sec[3 * i + 2];
+                T x0 = W.xr[i * 19 + lane];
+                T x1 = W.xr[(15 - i) * 19 + lane];
+                T x2 = W.xr[(16 + i) * 19 + lane];
+                T x3 = W.xr[(31 - i) * 19 + lane];
+                T t0 = V::add(x0, x3);
+                T t1 = V::add(x1, x2);
+                T t2 = V::muls(V::sub(x1, x2), c_sec[3 * i + 0]);
+                T t3 = V::muls(V::sub(x0, x3), c_sec[3 * i + 1]);
+                t[0][i] = V::add(t0, t1);
+                t[1][i] = V::muls(V::sub(t0, t1), c_sec[3 * i + 2]);
+                t[2][i] = V::add(t3, t2);
+                t[3][i] = V::muls(V::sub(t3, t2), c_sec[3 * i + 2]);
             }
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                float x0 = t[r][0], x1 = t[r][1], x2 = t[r][2], x3 = t[r][3], x4 = t[r][4], x5 = t[r][5], x6 = t[r][6], x7 = t[r][7], xt;
-                xt = x0 - x7; x0 += x7;
-                x7 = x1 - x6; x1 += x6;
-                x6 = x2 - x5; x2 += x5;
-                x5 = x3 - x4; x3 += x4;
-                x4 = x0 - x3; x0 += x3;
-                x3 = x1 - x2; x1 += x2;
-                t[r][0] = x0 + x1;
-                t[r][4] = (x0 - x1) * 0.70710677f;
-                x5 = x5 + x6;
-                x6 = (x6 + x7) * 0.70710677f;
-                x7 = x7 + xt;
-                x3 = (x3 + x4) * 0.70710677f;
-                x5 -= x7 * 0.198912367f;
-                x7 += x5 * 0.382683432f;
-                x5 -= x7 * 0.198912367f;
-                x0 = xt - x6; xt += x6;
-                t[r][1] = (xt + x7) * 0.50979561f;
-                t[r][2] = (x4 + x3) * 0.54119611f;
-                t[r][3] = (x0 - x5) * 0.60134488f;
-                t[r][5] = (x0 + x5) * 0.89997619f;
-                t[r][6] = (x4 - x3) * 1.30656302f;
-                t[r][7] = (xt - x7) * 2.56291556f;
+                T x0 = t[r][0], x1 = t[r][1], x2 = t[r][2], x3 = t[r][3], x4 = t[r][4], x5 = t[r][5], x6 = t[r][6], x7 = t[r][7], xt;
+                xt = V::sub(x0, x7); x0 = V::add(x0, x7);
+                x7 = V::sub(x1, x6); x1 = V::add(x1, x6);
+                x6 = V::sub(x2, x5); x2 = V::add(x2, x5);
+                x5 = V::sub(x3, x4); x3 = V::add(x3, x4);
+                x4 = V::sub(x0, x3); x0 = V::add(x0, x3);
+                x3 = V::sub(x1, x2); x1 = V::add(x1, x2);
+                t[r][0] = V::add(x0, x1);
+                t[r][4] = V::muls(V::sub(x0, x1), 0.70710677f);
+                x5 = V::add(x5, x6);
+                x6 = V::muls(V::add(x6, x7), 0.70710677f);
+                x7 = V::add(x7, xt);
+                x3 = V::muls(V::add(x3, x4), 0.70710677f);
+                x5 = V::sub(x5, V::muls(x7, 0.198912367f));
+                x7 = V::add(x7, V::muls(x5, 0.382683432f));
+                x5 = V::sub(x5, V::muls(x7, 0.198912367f));
+                x0 = V::sub(xt, x6); xt = V::add(xt, x6);
+                t[r][1] = V::muls(V::add(xt, x7), 0.50979561f);
+                t[r][2] = V::muls(V::add(x4, x3), 0.54119611f);
+                t[r][3] = V::muls(V::sub(x0, x5), 0.60134488f);
+                t[r][5] = V::muls(V::add(x0, x5), 0.89997619f);
+                t[r][6] = V::muls(V::sub(x4, x3), 1.30656302f);
+                t[r][7] = V::muls(V::sub(xt, x7), 2.56291556f);
             }
-            float* out = const_cast<float*>(drow(Dch, hbase + lane));
+            T* out = W.D + (15 + lane) * kDStride;
 #pragma unroll
             for (int i = 0; i < 7; i++) {
                 out[4 * i + 0] = t[0][i];
-                out[4 * i + 1] = t[2][i] + t[3][i] + t[3][i + 1];
-                out[4 * i + 2] = t[1][i] + t[1][i + 1];
-                out[4 * i + 3] = t[2][i + 1] + t[3][i] + t[3][i + 1];
+                out[4 * i + 1] = V::add(V::add(t[2][i], t[3][i]), t[3][i + 1]);
+                out[4 * i + 2] = V::add(t[1][i], t[1][i + 1]);
+                out[4 * i + 3] = V::add(V::add(t[2][i + 1], t[3][i]), t[3][i + 1]);
             }
             out[28] = t[0][7];
-            out[29] = t[2][7] + t[3][7];
+            out[29] = V::add(t[2][7], t[3][7]);
             out[30] = t[1][7];
             out[31] = t[3][7];
         }
-        dgc++;
-        __syncwarp();
-        if (mode == 1) continue;
+        __syncthreads();
 
         // ---------------- 512-tap window (minimp3.d:1305-1406) ----------------
-        {
-            const uint64_t gbase = (uint64_t)g * 576u * NCH;  // interleaved sample index of this granule's first sample
-            float* pcm = p.pcm + S.pcm_off;
-            const uint64_t skip = S.pcm_skip, count = S.pcm_count;
+        if (act && mode == 2) {
+            const uint64_t f0 = (uint64_t)g * 576u;   // first frame of this granule in the decoded signal
+            const bool inside = f0 >= skipf && f0 + 576u <= skipf + countf;
+            T* const out = pcm + (f0 - skipf);        // only dereferenced for delivered frames
             const float scale = 1.0f / 32768.0f;
-            // main part: lane (par, ii) produces samples 15-ii and 17+ii of slots s = 2q + par
             if (ii < 15) {
-                float V[32];
-                // V[j] = D[slot (j - 15 + par)][ j odd ? 31-ii : 1+ii ]   (rows of the reference's zlin)
+                // lane (par, ii) produces samples 15-ii and 17+ii of slots s = 2q + par.
+                // V[j] = D[row par + j][ j odd ? 31-ii : 1+ii ]  -- row r of D is slot r-15 ("window")
+                T Vw[32];
+                const T* base_lo = W.D + par * kDStride + (1 + ii);
+                const T* base_hi = W.D + par * kDStride + (31 - ii);
 #pragma unroll
-                for (int j = 0; j < 16; j++)
-                    V[j] = drow(Dch, hbase + par + j - 15)[(j & 1) ? 31 - ii : 1 + ii];
+                for (int j = 0; j < 16; j++) Vw[j] = (j & 1) ? base_hi[j * kDStride] : base_lo[j * kDStride];
 #pragma unroll
                 for (int q = 0; q < 9; q++) {
                     if (q > 0) {
-                        V[2 * q + 14] = drow(Dch, hbase + par + 2 * q - 1)[1 + ii];
-                        V[2 * q + 15] = drow(Dch, hbase + par + 2 * q)[31 - ii];
+                        Vw[2 * q + 14] = base_lo[(2 * q + 14) * kDStride];
+                        Vw[2 * q + 15] = base_hi[(2 * q + 15) * kDStride];
                     }
-                    float a, b;
+                    T a, b;
                     {
-                        const float vz = V[2 * q + 15], vy = V[2 * q + 0];
-                        b = vz * w1[0] + vy * w0[0];
-                        a = vz * w0[0] - vy * w1[0];
+                        const T vz = Vw[2 * q + 15], vy = Vw[2 * q + 0];
+                        b = V::add(V::muls(vz, w1[0]), V::muls(vy, w0[0]));
+                        a = V::sub(V::muls(vz, w0[0]), V::muls(vy, w1[0]));
                     }
 #pragma unroll
                     for (int k = 1; k < 8; k++) {
-                        const float vz = V[2 * q + 15 - k], vy = V[2 * q + k];
-                        b += vz * w1[k] + vy * w0[k];
-                        if (k & 1) a += vy * w1[k] - vz * w0[k];
-                        else a += vz * w0[k] - vy * w1[k];
+                        const T vz = Vw[2 * q + 15 - k], vy = Vw[2 * q + k];
+                        b = V::add(b, V::add(V::muls(vz, w1[k]), V::muls(vy, w0[k])));
+                        if (k & 1) a = V::add(a, V::sub(V::muls(vy, w1[k]), V::muls(vz, w0[k])));
+                        else a = V::add(a, V::sub(V::muls(vz, w0[k]), V::muls(vy, w1[k])));
                     }
                     const int s = 2 * q + par;
-                    const uint64_t ea = gbase + (uint64_t)((32 * s + 15 - ii) * NCH + ch);
-                    const uint64_t eb = gbase + (uint64_t)((32 * s + 17 + ii) * NCH + ch);
-                    if (ea >= skip && ea - skip < count) pcm[ea - skip] = a * scale;
-                    if (eb >= skip && eb - skip < count) pcm[eb - skip] = b * scale;
+                    const int fa = 32 * s + 15 - ii, fb = 32 * s + 17 + ii;
+                    if (inside || (f0 + fa >= skipf && f0 + fa - skipf < countf)) out[fa] = V::muls(a, scale);
+                    if (inside || (f0 + fb >= skipf && f0 + fb - skipf < countf)) out[fb] = V::muls(b, scale);
                 }
             }
             // samples 0 and 16 of every slot (mp3d_synth_pair), one slot per lane
             if (lane < 18) {
-                float z[15];
+                const T* col = W.D + lane * kDStride;   // row lane + k is slot lane - 15 + k
+                T z[15];
 #pragma unroll
-                for (int k = 0; k < 15; k++) z[k] = drow(Dch, hbase + lane - 15 + k)[16];
-                float a;
-                a = (z[14] - z[0]) * 29.0f;
-                a += (z[1] + z[13]) * 213.0f;
-                a += (z[12] - z[2]) * 459.0f;
-                a += (z[3] + z[11]) * 2037.0f;
-                a += (z[10] - z[4]) * 5153.0f;
-                a += (z[5] + z[9]) * 6574.0f;
-                a += (z[8] - z[6]) * 37489.0f;
-                a += z[7] * 75038.0f;
-                const uint64_t e0 = gbase + (uint64_t)((32 * lane) * NCH + ch);
-                if (e0 >= skip && e0 - skip < count) pcm[e0 - skip] = a * scale;
+                for (int k = 0; k < 15; k++) z[k] = col[k * kDStride + 16];
+                T a;
+                a = V::muls(V::sub(z[14], z[0]), 29.0f);
+                a = V::add(a, V::muls(V::add(z[1], z[13]), 213.0f));
+                a = V::add(a, V::muls(V::sub(z[12], z[2]), 459.0f));
+                a = V::add(a, V::muls(V::add(z[3], z[11]), 2037.0f));
+                a = V::add(a, V::muls(V::sub(z[10], z[4]), 5153.0f));
+                a = V::add(a, V::muls(V::add(z[5], z[9]), 6574.0f));
+                a = V::add(a, V::muls(V::sub(z[8], z[6]), 37489.0f));
+                a = V::add(a, V::muls(z[7], 75038.0f));
+                const int fa = 32 * lane, fb = 32 * lane + 16;
+                if (inside || (f0 + fa >= skipf && f0 + fa - skipf < countf)) out[fa] = V::muls(a, scale);
 #pragma unroll
-                for (int k = 0; k < 15; k += 2) z[k] = drow(Dch, hbase + lane - 15 + k)[0];
-                a = z[14] * 104.0f;
-                a += z[12] * 1567.0f;
-                a += z[10] * 9727.0f;
-                a += z[8] * 64019.0f;
-                a += z[6] * -9975.0f;
-                a += z[4] * -45.0f;
-                a += z[2] * 146.0f;
-                a += z[0] * -5.0f;
-                const uint64_t e16 = gbase + (uint64_t)((32 * lane + 16) * NCH + ch);
-                if (e16 >= skip && e16 - skip < count) pcm[e16 - skip] = a * scale;
+                for (int k = 0; k < 15; k += 2) z[k] = col[k * kDStride];
+                a = V::muls(z[14], 104.0f);
+                a = V::add(a, V::muls(z[12], 1567.0f));
+                a = V::add(a, V::muls(z[10], 9727.0f));
+                a = V::add(a, V::muls(z[8], 64019.0f));
+                a = V::add(a, V::muls(z[6], -9975.0f));
+                a = V::add(a, V::muls(z[4], -45.0f));
+                a = V::add(a, V::muls(z[2], 146.0f));
+                a = V::add(a, V::muls(z[0], -5.0f));
+                if (inside || (f0 + fb >= skipf && f0 + fb - skipf < countf)) out[fb] = V::muls(a, scale);
             }
         }
-        __syncwarp();
+        // slide the history: the last 15 slots become rows 0..14 (qmf_state, minimp3.d:1423-1433)
+        if (act && mode >= 1) {
+            __syncwarp();
+            T tmp[16];
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const int e = lane + 32 * m;
+                if (e < 15 * kDStride) tmp[m] = W.D[18 * kDStride + e];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const int e = lane + 32 * m;
+                if (e < 15 * kDStride) W.D[e] = tmp[m];
+            }
+            __syncwarp();
+        }
     }
 }
 
-template __global__ void l3_granule_kernel<1>(BatchParams, const Tile*, uint32_t);
-template __global__ void l3_granule_kernel<2>(BatchParams, const Tile*, uint32_t);
+template <int NCH, int WARPS>
+static void launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n, cudaStream_t s) {
+    if (!n) return;
+    static bool configured = false;
+    const size_t smem = 528 + (size_t)WARPS * sizeof(WarpSmem<NCH>);
+    if (!configured) {
+        cudaFuncSetAttribute(l3_granule_kernel<NCH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    l3_granule_kernel<NCH, WARPS><<<(n + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(p, tiles, n);
+}
 
 void launch_entropy(const BatchParams& p, cudaStream_t s) {
     if (!p.n_grch) return;
@@ -826,9 +1003,9 @@ void launch_entropy(const BatchParams& p, cudaStream_t s) {
 
 void launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
                     uint32_t n_mono, cudaStream_t s, cudaEvent_t ev_mid) {
-    if (n_stereo) l3_granule_kernel<2><<<n_stereo, 64, 0, s>>>(p, tiles_stereo, n_stereo);
+    launch_granule_t<2, kGranuleWarpsStereo>(p, tiles_stereo, n_stereo, s);
     if (ev_mid) cudaEventRecord(ev_mid, s);
-    if (n_mono) l3_granule_kernel<1><<<n_mono, 32, 0, s>>>(p, tiles_mono, n_mono);
+    launch_granule_t<1, kGranuleWarpsMono>(p, tiles_mono, n_mono, s);
 }
 
 }  // namespace l3b

@@ -24,9 +24,7 @@ namespace l3b {
 constexpr int kSfRecBytes = 96;    // per granule-channel: iscf[40] ist_pos[40] nz_chunks(u16) pad
 constexpr int kIsChunks = 72;      // 576 int16 = 72 x 16 bytes
 constexpr int kTileGranules = 32;  // granules per CTA tile of the granule kernel (2-granule recompute halo)
-constexpr int kXrStride = 608;     // per-channel spectrum buffer: 576 natural layout / 32x19 padded layout
-constexpr int kDParity = 624;      // floats per (channel, slot parity) history array: 18 rows x 33 (+30 pad so that
-                                   // the two parities sit 16 banks apart)
+constexpr int kXrStride = 608;     // spectrum buffer elements: 576 in natural layout / 32x19 in the padded layout
 
 struct Tile {
     uint32_t stream, g0, ng;
@@ -59,8 +57,11 @@ struct BatchParams {
     DeviceTables t;
 };
 
+constexpr int kGranuleWarpsStereo = 12;  // warps (= tiles) per CTA of the granule kernel, one CTA per SM
+constexpr int kGranuleWarpsMono = 16;
+
 __global__ void l3_entropy_kernel(BatchParams p);
-template <int NCH>
+template <int NCH, int WARPS>
 __global__ void l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles);
 
 void launch_entropy(const BatchParams& p, cudaStream_t s);
