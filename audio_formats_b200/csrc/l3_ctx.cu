@@ -112,7 +112,7 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** out) {
     uint8_t* base = static_cast<uint8_t*>(c->d_tables);
     c->t.huff = reinterpret_cast<const uint16_t*>(base + o_huff);
     c->t.huff_entries = (uint32_t)hl.entries.size();
-    for (int i = 0; i < 16; i++) { c->t.huff_base[i] = hl.base[i]; c->t.huff_root[i] = hl.root_bits[i]; }
+    for (int i = 0; i < 18; i++) { c->t.huff_base[i] = hl.base[i]; c->t.huff_root[i] = hl.root_bits[i]; }
     c->t.count1 = base + o_c1;
     c->t.sfb_of_pair = base + o_pair;
     c->t.sfb_width = base + o_w;

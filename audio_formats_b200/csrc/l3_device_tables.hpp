@@ -11,13 +11,15 @@ namespace l3b {
 
 // ---- Huffman decode LUT (our own layout) ---------------------------------------------------------
 // 16-bit entries, per book a root table of 2^root_bits entries followed by its sub-tables.
-//   leaf : bit15 = 0 : [len:4 @8][v1:4 @4][v0:4 @0]     len = bits consumed at THIS level (1..8, or 0 for the zero book)
+//   leaf : bit15 = 0 : [v3:1 @13][v2:1 @12][len:4 @8][v1:4 @4][v0:4 @0]   len = bits consumed at THIS level (0..8)
 //   link : bit15 = 1 : [width-1:3 @12][offset:12 @0]    offset relative to the book's base
 // Book 15 (index L3_NBOOKS) is the all-zero book used by table_select 0/4/14 (minimp3.d:768: tabindex 0).
+// Books 16 and 17 are the count1 books A and B (minimp3.d:766-767) as 6-bit root tables in the same leaf format:
+// v0..v3 are the non-zero flags of the quad, so the pair decoder treats a quad as two pairs of 0/1 magnitudes.
 struct HuffLut {
     std::vector<uint16_t> entries;
-    uint16_t base[L3_NBOOKS + 1];
-    uint8_t root_bits[L3_NBOOKS + 1];
+    uint16_t base[L3_NBOOKS + 3];
+    uint8_t root_bits[L3_NBOOKS + 3];
     uint8_t count1[2][64];  // 6-bit peek -> flags<<4 | len
 };
 
@@ -71,6 +73,19 @@ inline HuffLut build_huff_lut() {
     L.root_bits[L3_NBOOKS] = 1;
     L.entries.push_back(0);
     L.entries.push_back(0);
+    for (int t = 0; t < 2; t++) {
+        L.base[L3_NBOOKS + 1 + t] = (uint16_t)L.entries.size();
+        L.root_bits[L3_NBOOKS + 1 + t] = 6;
+        for (int v = 0; v < 64; v++) {
+            uint16_t e = 0;
+            for (int f = 0; f < 16; f++) {
+                int ln = L3_C1LEN[t * 16 + f];
+                if ((v >> (6 - ln)) == L3_C1CODE[t * 16 + f])
+                    e = (uint16_t)((ln << 8) | ((f >> 3) & 1) | (((f >> 2) & 1) << 4) | (((f >> 1) & 1) << 12) | ((f & 1) << 13));
+            }
+            L.entries.push_back(e);
+        }
+    }
     memset(L.count1, 0, sizeof L.count1);
     for (int t = 0; t < 2; t++)
         for (int v = 0; v < 64; v++)

@@ -1,6 +1,8 @@
 // l3_kernels.cu -- see l3_kernels.cuh.  Compile with -fmad=false (bit-exactness contract).
 #include "l3_kernels.cuh"
 
+#include <cstdlib>
+
 #include "l3_tables_gen.h"
 
 namespace l3b {
@@ -123,13 +125,13 @@ __device__ __forceinline__ uint32_t find_stream(const l3b_stream_desc_t* streams
 
 __global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
     extern __shared__ uint16_t s_lut[];  // huff entries, then 128 bytes of count1
-    uint8_t* s_c1 = reinterpret_cast<uint8_t*>(s_lut + ((p.t.huff_entries + 7) & ~7u));
     for (uint32_t i = threadIdx.x; i < p.t.huff_entries; i += blockDim.x) s_lut[i] = p.t.huff[i];
-    for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) s_c1[i] = p.t.count1[i];
     __syncthreads();
 
-    const uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= p.n_grch) return;
+    uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = gi < p.n_grch;
+    if (__all_sync(0xffffffffu, !live)) return;
+    if (!live) gi = p.n_grch - 1;  // tail lanes of the last warp shadow its last granule-channel in lockstep
     const uint32_t si = find_stream(p.streams, p.n_streams, gi);
     const l3b_stream_desc_t* S = p.streams + si;
     const int nch = S->nch;
@@ -231,30 +233,36 @@ __global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
     }
 
     // ---------------- Huffman (minimp3.d:748-883), values only ----------------
+    // One PAIR of values per loop iteration in every lane, so the lanes of a warp stay on the same
+    // instructions: big_values pairs use the region's book; a count1 quad is decoded as two consecutive
+    // pairs of 0/1 magnitudes (first half: code + v0,v1; second half: v2,v3 from the saved flags, through
+    // the zero-length book).  Sign bits follow the same rule in both (minimp3.d:819, 874-878).
     uint4* outp = p.is + gi * kIsChunks;
     uint4 q = make_uint4(0, 0, 0, 0);
     int idx = 0;
-#define L3_EMIT_PAIR(v0, v1)                                                                   \
-    do {                                                                                       \
-        uint32_t pk_ = ((uint32_t)(v0) & 0xFFFFu) | ((uint32_t)(v1) << 16);                    \
-        int pp_ = (idx >> 1) & 3;                                                              \
-        if (pp_ == 0) q.x = pk_; else if (pp_ == 1) q.y = pk_; else if (pp_ == 2) q.z = pk_;   \
-        else { q.w = pk_; outp[idx >> 3] = q; q = make_uint4(0, 0, 0, 0); }                    \
-        idx += 2;                                                                              \
-    } while (0)
-
     const int bv_end = 2 * d.big_values();
-    for (int r = 0; r < 3 && idx < bv_end; r++) {
-        int rend = r == 0 ? d.region1_start() : (r == 1 ? d.region2_start() : 576);
-        if (rend > bv_end) rend = bv_end;
+    const int r1 = d.region1_start(), r2 = d.region2_start();
+    // per-region book parameters: base | root<<16 | linbits<<24
+    uint32_t par[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
         const int sel = d.table_select(r);
         const int book = c_sel2book[sel] < 0 ? L3_NBOOKS : c_sel2book[sel];
-        const int linbits = c_linbits[sel];
-        const uint32_t base = p.t.huff_base[book];
-        const int rootw = p.t.huff_root[book];
-        while (idx < rend) {
+        par[r] = (uint32_t)p.t.huff_base[book] | ((uint32_t)p.t.huff_root[book] << 16) | ((uint32_t)c_linbits[sel] << 24);
+    }
+    const uint32_t par_c1 = (uint32_t)p.t.huff_base[L3_NBOOKS + 1 + d.count1_table()] | (6u << 16);
+    const uint32_t par_zero = (uint32_t)p.t.huff_base[L3_NBOOKS] | (1u << 16);
+    bool done = false;
+    uint32_t pend = 0;  // bit 2: second half of a quad pending; bits 0,1: its v2,v3 flags
+    while (__any_sync(0xffffffffu, !done)) {
+        if (!done) {
+            const bool in_big = idx < bv_end;
+            const bool second = !in_big && (pend & 4u);
+            const uint32_t pr = in_big ? (idx < r1 ? par[0] : (idx < r2 ? par[1] : par[2])) : (second ? par_zero : par_c1);
+            const uint32_t base = pr & 0xFFFFu;
+            const int linbits = (int)(pr >> 24);
             br.refill();
-            int w = rootw;
+            int w = (int)((pr >> 16) & 0xFF);
             uint32_t e = s_lut[base + br.peek(w)];
             while (e & 0x8000u) {
                 br.skip(w);
@@ -263,32 +271,32 @@ __global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
             }
             br.skip((int)((e >> 8) & 15));
             int a0 = (int)(e & 15), a1 = (int)((e >> 4) & 15);
-            if (linbits && a0 == 15) { br.refill(); a0 += (int)br.peek(linbits); br.skip(linbits); }
-            if (a0) { if (br.peek(1)) a0 = -a0; br.skip(1); }
-            if (linbits && a1 == 15) { br.refill(); a1 += (int)br.peek(linbits); br.skip(linbits); }
-            if (a1) { if (br.peek(1)) a1 = -a1; br.skip(1); }
-            L3_EMIT_PAIR(a0, a1);
+            if (!in_big) {
+                if (!second) {
+                    // first half of a quad: limit tested after the code, before the signs (minimp3.d:866);
+                    // then the sfb terminator (minimp3.d:873)
+                    if (br.pos > limit || idx >= 576) done = true;
+                    pend = 4u | ((e >> 12) & 3u);
+                } else {
+                    if (idx >= 576) done = true;  // (minimp3.d:876)
+                    a0 = (int)(pend & 1u);
+                    a1 = (int)((pend >> 1) & 1u);
+                    pend = 0;
+                }
+            }
+            if (!done) {
+                if (linbits && a0 == 15) { br.refill(); a0 += (int)br.peek(linbits); br.skip(linbits); }
+                if (a0) { if (br.peek(1)) a0 = -a0; br.skip(1); }
+                if (linbits && a1 == 15) { br.refill(); a1 += (int)br.peek(linbits); br.skip(linbits); }
+                if (a1) { if (br.peek(1)) a1 = -a1; br.skip(1); }
+                const uint32_t pk = ((uint32_t)a0 & 0xFFFFu) | ((uint32_t)a1 << 16);
+                const int pp = (idx >> 1) & 3;
+                if (pp == 0) q.x = pk; else if (pp == 1) q.y = pk; else if (pp == 2) q.z = pk;
+                else { q.w = pk; outp[idx >> 3] = q; q = make_uint4(0, 0, 0, 0); }
+                idx += 2;
+            }
         }
     }
-    {
-        const uint8_t* c1 = s_c1 + 64 * d.count1_table();
-        for (;;) {
-            br.refill();
-            uint32_t e = c1[br.peek(6)];
-            br.skip((int)(e & 15));
-            if (br.pos > limit) break;  // tested after the code, before the signs (minimp3.d:866)
-            if (idx >= 576) break;      // sfb terminator (minimp3.d:873)
-            int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-            if (e & 0x80) { v0 = br.peek(1) ? -1 : 1; br.skip(1); }
-            if (e & 0x40) { v1 = br.peek(1) ? -1 : 1; br.skip(1); }
-            L3_EMIT_PAIR(v0, v1);
-            if (idx >= 576) break;      // (minimp3.d:876)
-            if (e & 0x20) { v2 = br.peek(1) ? -1 : 1; br.skip(1); }
-            if (e & 0x10) { v3 = br.peek(1) ? -1 : 1; br.skip(1); }
-            L3_EMIT_PAIR(v2, v3);
-        }
-    }
-#undef L3_EMIT_PAIR
     int chunks = (idx + 7) >> 3;
     if ((idx >> 1) & 3) outp[idx >> 3] = q;
     if (p.zero_fill)
@@ -366,10 +374,12 @@ __device__ __noinline__ float pow43_big(const float* pow43, int x) {
     return pow43[(x + sign) >> 6] * (1.0f + frac * ((4.0f / 3) + frac * (2.0f / 9))) * (float)mult;
 }
 
-__device__ __forceinline__ float requant(const float* pow43, int v, float s) {
+// s_pow43s[v + 128] = sign(v) * |v|^(4/3) for -128 <= v <= 128: the reference's own trick of a mirrored table
+// (minimp3.d:722-725, 816), extended to the whole table range.  (-p)*s == -(p*s) exactly.
+__device__ __forceinline__ float requant(const float* pow43s, int v, float s) {
+    if ((unsigned)(v + 128) <= 256u) return __fmul_rn(pow43s[v + 128], s);
     int a = v < 0 ? -v : v;
-    float pw = a < 129 ? pow43[a] : pow43_big(pow43, a);
-    float r = __fmul_rn(pw, s);
+    float r = __fmul_rn(pow43_big(pow43s + 128, a), s);
     return v < 0 ? -r : r;
 }
 
@@ -526,8 +536,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // per-warp shared memory
 template <int NCH>
 struct __align__(16) WarpSmem {
-    typename VT<NCH>::T xr[kXrStride];         // spectrum (natural layout) / IMDCT output (x19 padded layout)
-    typename VT<NCH>::T D[kDRows * kDStride];  // DCT-32 outputs: rows 0..14 history, 15..32 this granule
+    // DCT-32 outputs, 33 rows x 33: rows 0..14 are the history (qmf_state), rows 15..32 belong to the current
+    // granule.  The current-granule rows ALIAS the spectrum buffer `xr` (natural layout while requantising,
+    // x19 padded layout between IMDCT and DCT): each stage has consumed its input before the next one writes.
+    typename VT<NCH>::T Dbuf[1 + 15 * kDStride + kXrStride];  // D = Dbuf + 1, so that row 15 (= xr) is 16-byte aligned
     uint4 st_is[NCH * kIsChunks];              // TMA-staged inputs of the next granule: quantised spectra,
     uint4 st_rec[NCH * kSfRecBytes / 16];      //   scalefactor records,
     uint4 st_desc[NCH];                        //   descriptors
@@ -559,15 +571,20 @@ __device__ __noinline__ void imdct_split(float2* x, float2* ovl, float2* y, bool
 __device__ __forceinline__ void imdct_split(float*, float*, float*, bool, bool, int, int) {}
 
 template <int NCH, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
+__global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
     typedef VT<NCH> V;
     typedef typename V::T T;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    float* s_pow43 = reinterpret_cast<float*>(smem_raw);  // 132 floats, shared by the CTA
+    float* s_pow43 = reinterpret_cast<float*>(smem_raw);  // 257 signed entries (+pad), shared by the CTA
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem<NCH>& W = *reinterpret_cast<WarpSmem<NCH>*>(smem_raw + 528 + (size_t)warp * sizeof(WarpSmem<NCH>));
+    WarpSmem<NCH>& W = *reinterpret_cast<WarpSmem<NCH>*>(smem_raw + 1040 + (size_t)warp * sizeof(WarpSmem<NCH>));
+    T* const D = W.Dbuf + 1;
+    T* const xr = D + 15 * kDStride;
 
-    for (int i = threadIdx.x; i < 129; i += 32 * WARPS) s_pow43[i] = p.t.pow43[i];
+    for (int i = threadIdx.x; i < 257; i += 32 * WARPS) {
+        const float pw = p.t.pow43[i < 128 ? 128 - i : i - 128];
+        s_pow43[i] = i < 128 ? -pw : pw;
+    }
 
     const uint32_t tile_idx = blockIdx.x * WARPS + warp;
     const bool have_tile = tile_idx < n_tiles;
@@ -578,7 +595,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
 
     for (int i = lane; i < 3 * 288 / 4; i += 32)
         reinterpret_cast<uint32_t*>(&W.sfbpair[0][0])[i] = reinterpret_cast<const uint32_t*>(p.t.sfb_of_pair + row * 3 * 288)[i];
-    for (int i = lane; i < 15 * kDStride; i += 32) W.D[i] = V::zero();
+    for (int i = lane; i < 15 * kDStride; i += 32) D[i] = V::zero();
     if (lane == 0) mbar_init(&W.mbar, 1);
 
     // synthesis window weights of this lane: inner index ii = lane & 15 (0..14 active), slot parity par
@@ -638,7 +655,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
             if (d0.reset_before() && it != 0) {
 #pragma unroll
                 for (int i = 0; i < 9; i++) ovl[i] = V::zero();
-                for (int i = lane; i < 15 * kDStride; i += 32) W.D[i] = V::zero();
+                for (int i = lane; i < 15 * kDStride; i += 32) D[i] = V::zero();
             }
             kind0 = d0.kind(); kind1 = d1.kind();
             hb = d0.hdr_bits();
@@ -691,9 +708,9 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
                             const float l1 = __fadd_rn(a1, b1), r1 = __fsub_rn(a1, b1);
                             a0 = l0; b0 = r0; a1 = l1; b1 = r1;
                         }
-                        *reinterpret_cast<float4*>(&W.xr[2 * pi]) = make_float4(a0, b0, a1, b1);
+                        *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(a0, b0, a1, b1);
                     } else {
-                        *reinterpret_cast<float2*>(&W.xr[2 * pi]) = make_float2(a0, a1);
+                        *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(a0, a1);
                     }
                 }
             }
@@ -706,7 +723,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
 
             // ---------------- intensity stereo (minimp3.d:898-982), on channel 0's band layout ----------------
             if (NCH == 2 && istereo) {
-                float2* X = reinterpret_cast<float2*>(W.xr);
+                float2* X = reinterpret_cast<float2*>(xr);
                 const int n_long_sfb0 = kind0 == 0 ? 22 : (kind0 == 1 ? 0 : (mpeg1 ? 8 : 6));
                 const int n_sfb0 = n_long_sfb0 + (kind0 == 0 ? 0 : (kind0 == 1 ? 39 : 30));
                 const uint8_t* sfbw = p.t.sfb_width + (row * 3 + kind0) * 40;
@@ -780,12 +797,12 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
             const int nlb0 = kind0 == 2 ? n_long_bands_mixed : 0, nlb1 = kind1 == 2 ? n_long_bands_mixed : 0;
             if (kind0 == 0 && kind1 == 0) {
 #pragma unroll
-                for (int i = 0; i < 18; i++) x[i] = W.xr[lane * 18 + i];
+                for (int i = 0; i < 18; i++) x[i] = xr[lane * 18 + i];
             } else {
                 // short / mixed blocks: L3_reorder folded into the load through the permutation table
                 const uint16_t* pm0 = p.t.perm + (row * 2 + (kind0 == 2 ? 1 : 0)) * 576 + lane * 18;
                 const uint16_t* pm1 = p.t.perm + (row * 2 + (kind1 == 2 ? 1 : 0)) * 576 + lane * 18;
-                const float* xf = reinterpret_cast<const float*>(W.xr);
+                const float* xf = reinterpret_cast<const float*>(xr);
 #pragma unroll
                 for (int i = 0; i < 18; i++) {
                     const int i0 = kind0 == 0 ? lane * 18 + i : (int)__ldg(pm0 + i);
@@ -829,7 +846,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
                     for (int i = 1; i < 18; i += 2) y[i] = V::neg(y[i]);
                 }
 #pragma unroll
-                for (int i = 0; i < 18; i++) W.xr[lane * 19 + i] = y[i];
+                for (int i = 0; i < 18; i++) xr[lane * 19 + i] = y[i];
             }
         }
         __syncthreads();
@@ -839,10 +856,10 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
             T t[4][8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                T x0 = W.xr[i * 19 + lane];
-                T x1 = W.xr[(15 - i) * 19 + lane];
-                T x2 = W.xr[(16 + i) * 19 + lane];
-                T x3 = W.xr[(31 - i) * 19 + lane];
+                T x0 = xr[i * 19 + lane];
+                T x1 = xr[(15 - i) * 19 + lane];
+                T x2 = xr[(16 + i) * 19 + lane];
+                T x3 = xr[(31 - i) * 19 + lane];
                 T t0 = V::add(x0, x3);
                 T t1 = V::add(x1, x2);
                 T t2 = V::muls(V::sub(x1, x2), c_sec[3 * i + 0]);
@@ -852,6 +869,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
                 t[2][i] = V::add(t3, t2);
                 t[3][i] = V::muls(V::sub(t3, t2), c_sec[3 * i + 2]);
             }
+            __syncwarp(0x3FFFFu);  // all 18 slots have read their column: the buffer may now take the output rows
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 T x0 = t[r][0], x1 = t[r][1], x2 = t[r][2], x3 = t[r][3], x4 = t[r][4], x5 = t[r][5], x6 = t[r][6], x7 = t[r][7], xt;
@@ -878,7 +896,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
                 t[r][6] = V::muls(V::sub(x4, x3), 1.30656302f);
                 t[r][7] = V::muls(V::sub(xt, x7), 2.56291556f);
             }
-            T* out = W.D + (15 + lane) * kDStride;
+            T* out = D + (15 + lane) * kDStride;
 #pragma unroll
             for (int i = 0; i < 7; i++) {
                 out[4 * i + 0] = t[0][i];
@@ -903,8 +921,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
                 // lane (par, ii) produces samples 15-ii and 17+ii of slots s = 2q + par.
                 // V[j] = D[row par + j][ j odd ? 31-ii : 1+ii ]  -- row r of D is slot r-15 ("window")
                 T Vw[32];
-                const T* base_lo = W.D + par * kDStride + (1 + ii);
-                const T* base_hi = W.D + par * kDStride + (31 - ii);
+                const T* base_lo = D + par * kDStride + (1 + ii);
+                const T* base_hi = D + par * kDStride + (31 - ii);
 #pragma unroll
                 for (int j = 0; j < 16; j++) Vw[j] = (j & 1) ? base_hi[j * kDStride] : base_lo[j * kDStride];
 #pragma unroll
@@ -934,7 +952,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
             }
             // samples 0 and 16 of every slot (mp3d_synth_pair), one slot per lane
             if (lane < 18) {
-                const T* col = W.D + lane * kDStride;   // row lane + k is slot lane - 15 + k
+                const T* col = D + lane * kDStride;   // row lane + k is slot lane - 15 + k
                 T z[15];
 #pragma unroll
                 for (int k = 0; k < 15; k++) z[k] = col[k * kDStride + 16];
@@ -969,13 +987,13 @@ __global__ void __launch_bounds__(32 * WARPS, 1) l3_granule_kernel(BatchParams p
 #pragma unroll
             for (int m = 0; m < 16; m++) {
                 const int e = lane + 32 * m;
-                if (e < 15 * kDStride) tmp[m] = W.D[18 * kDStride + e];
+                if (e < 15 * kDStride) tmp[m] = D[18 * kDStride + e];
             }
             __syncwarp();
 #pragma unroll
             for (int m = 0; m < 16; m++) {
                 const int e = lane + 32 * m;
-                if (e < 15 * kDStride) W.D[e] = tmp[m];
+                if (e < 15 * kDStride) D[e] = tmp[m];
             }
             __syncwarp();
         }
@@ -986,7 +1004,7 @@ template <int NCH, int WARPS>
 static void launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n, cudaStream_t s) {
     if (!n) return;
     static bool configured = false;
-    const size_t smem = 528 + (size_t)WARPS * sizeof(WarpSmem<NCH>);
+    const size_t smem = 1040 + (size_t)WARPS * sizeof(WarpSmem<NCH>);
     if (!configured) {
         cudaFuncSetAttribute(l3_granule_kernel<NCH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
@@ -996,14 +1014,17 @@ static void launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n
 
 void launch_entropy(const BatchParams& p, cudaStream_t s) {
     if (!p.n_grch) return;
-    size_t smem = (size_t)((p.t.huff_entries + 7) & ~7u) * 2 + 128;
+    size_t smem = (size_t)((p.t.huff_entries + 7) & ~7u) * 2;
     unsigned blocks = (unsigned)((p.n_grch + 127) / 128);
     l3_entropy_kernel<<<blocks, 128, smem, s>>>(p);
 }
 
 void launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
                     uint32_t n_mono, cudaStream_t s, cudaEvent_t ev_mid) {
-    launch_granule_t<2, kGranuleWarpsStereo>(p, tiles_stereo, n_stereo, s);
+    static const int warps_env = getenv("L3B_GRANULE_WARPS") ? atoi(getenv("L3B_GRANULE_WARPS")) : kGranuleWarpsStereo;
+    if (warps_env == 8) launch_granule_t<2, 8>(p, tiles_stereo, n_stereo, s);
+    else if (warps_env == 4) launch_granule_t<2, 4>(p, tiles_stereo, n_stereo, s);
+    else launch_granule_t<2, kGranuleWarpsStereo>(p, tiles_stereo, n_stereo, s);
     if (ev_mid) cudaEventRecord(ev_mid, s);
     launch_granule_t<1, kGranuleWarpsMono>(p, tiles_mono, n_mono, s);
 }

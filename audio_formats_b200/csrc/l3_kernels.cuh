@@ -33,8 +33,8 @@ struct Tile {
 struct DeviceTables {
     const uint16_t* huff;       // HuffLut::entries
     uint32_t huff_entries;
-    uint16_t huff_base[16];
-    uint8_t huff_root[16];
+    uint16_t huff_base[18];     // books 0..14, 15 = all-zero book, 16/17 = count1 A/B
+    uint8_t huff_root[18];
     const uint8_t* count1;      // [2][64]
     const uint8_t* sfb_of_pair; // [8][3][288]
     const uint8_t* sfb_width;   // [8][3][40]
@@ -57,7 +57,7 @@ struct BatchParams {
     DeviceTables t;
 };
 
-constexpr int kGranuleWarpsStereo = 12;  // warps (= tiles) per CTA of the granule kernel, one CTA per SM
+constexpr int kGranuleWarpsStereo = 16;  // warps (= tiles) per CTA of the granule kernel, one CTA per SM
 constexpr int kGranuleWarpsMono = 16;
 
 __global__ void l3_entropy_kernel(BatchParams p);
