@@ -80,8 +80,10 @@ struct BitCursor {
     uint32_t nwords, next, pos;
     uint64_t cache;
     int nbits;
+    // nwords counts the 16 zero pad bytes that follow every stream, so clamping the index makes reads past
+    // the end return zero bits without a branch
     __device__ __forceinline__ uint32_t ldw(uint32_t i) const {
-        return i < nwords ? __byte_perm(__ldg(words + i), 0, 0x0123) : 0u;
+        return __byte_perm(__ldg(words + min(i, nwords - 1)), 0, 0x0123);
     }
     __device__ __forceinline__ void init(const uint32_t* w, uint32_t nw, uint32_t bitpos) {
         words = w; nwords = nw; pos = bitpos;
@@ -233,15 +235,13 @@ __global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
     }
 
     // ---------------- Huffman (minimp3.d:748-883), values only ----------------
-    // One PAIR of values per loop iteration in every lane, so the lanes of a warp stay on the same
-    // instructions: big_values pairs use the region's book; a count1 quad is decoded as two consecutive
-    // pairs of 0/1 magnitudes (first half: code + v0,v1; second half: v2,v3 from the saved flags, through
-    // the zero-length book).  Sign bits follow the same rule in both (minimp3.d:819, 874-878).
+    // One PAIR of values per step in every lane, four steps (one 16-byte chunk) per loop trip, so the lanes
+    // of a warp stay on the same straight-line code: big_values pairs use the region's book; a count1 quad
+    // is decoded as two consecutive pairs of 0/1 magnitudes (first half: code + v0,v1; second half: v2,v3
+    // from the saved flags, through the zero-length book).  Sign bits follow the same rule in both
+    // (minimp3.d:819, 874-878).
     uint4* outp = p.is + gi * kIsChunks;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    int idx = 0;
     const int bv_end = 2 * d.big_values();
-    const int r1 = d.region1_start(), r2 = d.region2_start();
     // per-region book parameters: base | root<<16 | linbits<<24
     uint32_t par[3];
 #pragma unroll
@@ -252,53 +252,89 @@ __global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
     }
     const uint32_t par_c1 = (uint32_t)p.t.huff_base[L3_NBOOKS + 1 + d.count1_table()] | (6u << 16);
     const uint32_t par_zero = (uint32_t)p.t.huff_base[L3_NBOOKS] | (1u << 16);
+
+    // 32-bit window over the bit stream: (w0:w1) are the words at wi, wi+1; pos is the absolute bit position
+    uint32_t pos = br.pos;
+    uint32_t wi = pos >> 5;
+    uint32_t w0 = br.ldw(wi), w1 = br.ldw(wi + 1);
+#define L3_PEEK32() __funnelshift_l(w1, w0, pos)
+#define L3_ADVANCE(n)                                                 \
+    do {                                                              \
+        pos += (uint32_t)(n);                                         \
+        if ((pos >> 5) != wi) { wi++; w0 = w1; w1 = br.ldw(wi + 1); } \
+    } while (0)
+
+    int idx = 0;
+    int nb = d.region1_start();      // next region boundary
+    uint32_t cur = par[0];
+    int reg = 0;
     bool done = false;
     uint32_t pend = 0;  // bit 2: second half of a quad pending; bits 0,1: its v2,v3 flags
-    while (__any_sync(0xffffffffu, !done)) {
-        if (!done) {
-            const bool in_big = idx < bv_end;
-            const bool second = !in_big && (pend & 4u);
-            const uint32_t pr = in_big ? (idx < r1 ? par[0] : (idx < r2 ? par[1] : par[2])) : (second ? par_zero : par_c1);
-            const uint32_t base = pr & 0xFFFFu;
-            const int linbits = (int)(pr >> 24);
-            br.refill();
-            int w = (int)((pr >> 16) & 0xFF);
-            uint32_t e = s_lut[base + br.peek(w)];
-            while (e & 0x8000u) {
-                br.skip(w);
-                w = (int)((e >> 12) & 7) + 1;
-                e = s_lut[base + (e & 0xFFFu) + br.peek(w)];
-            }
-            br.skip((int)((e >> 8) & 15));
-            int a0 = (int)(e & 15), a1 = (int)((e >> 4) & 15);
-            if (!in_big) {
-                if (!second) {
-                    // first half of a quad: limit tested after the code, before the signs (minimp3.d:866);
-                    // then the sfb terminator (minimp3.d:873)
-                    if (br.pos > limit || idx >= 576) done = true;
-                    pend = 4u | ((e >> 12) & 3u);
-                } else {
-                    if (idx >= 576) done = true;  // (minimp3.d:876)
-                    a0 = (int)(pend & 1u);
-                    a1 = (int)((pend >> 1) & 1u);
-                    pend = 0;
-                }
-            }
-            if (!done) {
-                if (linbits && a0 == 15) { br.refill(); a0 += (int)br.peek(linbits); br.skip(linbits); }
-                if (a0) { if (br.peek(1)) a0 = -a0; br.skip(1); }
-                if (linbits && a1 == 15) { br.refill(); a1 += (int)br.peek(linbits); br.skip(linbits); }
-                if (a1) { if (br.peek(1)) a1 = -a1; br.skip(1); }
-                const uint32_t pk = ((uint32_t)a0 & 0xFFFFu) | ((uint32_t)a1 << 16);
-                const int pp = (idx >> 1) & 3;
-                if (pp == 0) q.x = pk; else if (pp == 1) q.y = pk; else if (pp == 2) q.z = pk;
-                else { q.w = pk; outp[idx >> 3] = q; q = make_uint4(0, 0, 0, 0); }
-                idx += 2;
-            }
+    const int r2 = d.region2_start();
+
+    auto decode_pair = [&]() -> uint32_t {
+        const bool in_big = idx < bv_end;
+        if (in_big && idx >= nb) {   // region change (at most twice per granule-channel)
+            reg = idx < r2 ? 1 : 2;
+            cur = par[reg];
+            nb = reg == 1 ? r2 : 576;
+            if (reg == 1 && idx >= r2) { cur = par[2]; nb = 576; }
         }
+        const bool second = !in_big && (pend & 4u);
+        const bool first = !in_big && !second;
+        const uint32_t pr = in_big ? cur : (second ? par_zero : par_c1);
+        const uint32_t base = pr & 0xFFFFu;
+        const int linbits = (int)(pr >> 24);
+        int w = (int)((pr >> 16) & 0xFF);
+        uint32_t bits = L3_PEEK32();
+        uint32_t e = s_lut[base + (bits >> (32 - w))];
+        while (e & 0x8000u) {  // codes longer than the root table (rare)
+            L3_ADVANCE(w);
+            w = (int)((e >> 12) & 7) + 1;
+            bits = L3_PEEK32();
+            e = s_lut[base + (e & 0xFFFu) + (bits >> (32 - w))];
+        }
+        L3_ADVANCE((e >> 8) & 15);
+        // quad bookkeeping: the limit is tested after the code and before the signs (minimp3.d:866), then the
+        // sfb terminator before each half (minimp3.d:873, 876)
+        const bool stop = (first && pos > limit) || (!in_big && idx >= 576);
+        int a0 = second ? (int)(pend & 1u) : (int)(e & 15);
+        int a1 = second ? (int)((pend >> 1) & 1u) : (int)((e >> 4) & 15);
+        pend = first ? (4u | ((e >> 12) & 3u)) : 0u;
+        done = done || stop;
+        if (linbits && (a0 == 15 || a1 == 15)) {  // escapes (rare)
+            if (a0 == 15) { a0 += (int)(L3_PEEK32() >> (32 - linbits)); L3_ADVANCE(linbits); }
+            { const int n0 = a0 != 0; const int sg = n0 & (int)(L3_PEEK32() >> 31); L3_ADVANCE(n0); a0 = sg ? -a0 : a0; }
+            if (a1 == 15) { a1 += (int)(L3_PEEK32() >> (32 - linbits)); L3_ADVANCE(linbits); }
+            { const int n1 = a1 != 0; const int sg = n1 & (int)(L3_PEEK32() >> 31); L3_ADVANCE(n1); a1 = sg ? -a1 : a1; }
+        } else {
+            const int n0 = a0 != 0, n1 = a1 != 0;
+            const uint32_t two = L3_PEEK32() >> 30;
+            const int s0 = n0 & (int)(two >> 1);
+            const int s1 = n1 & (int)(two >> (1 - n0));
+            L3_ADVANCE(n0 + n1);
+            a0 = (a0 ^ -s0) + s0;
+            a1 = (a1 ^ -s1) + s1;
+        }
+        uint32_t pk = ((uint32_t)a0 & 0xFFFFu) | ((uint32_t)a1 << 16);
+        if (done) pk = 0; else idx += 2;
+        return pk;
+    };
+
+    while (__any_sync(0xffffffffu, !done)) {
+        // `done` lanes keep running the same code into dead registers (their pos/idx no longer matter)
+        const int at = idx >> 3;
+        const bool was_done = done;
+        uint4 q;
+        q.x = decode_pair();
+        q.y = decode_pair();
+        q.z = decode_pair();
+        q.w = decode_pair();
+        if (!was_done && at < kIsChunks) outp[at] = q;
     }
+#undef L3_PEEK32
+#undef L3_ADVANCE
     int chunks = (idx + 7) >> 3;
-    if ((idx >> 1) & 3) outp[idx >> 3] = q;
     if (p.zero_fill)
         for (int c = chunks; c < kIsChunks; c++) outp[c] = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint16_t*>(rec + 80) = (uint16_t)chunks;
