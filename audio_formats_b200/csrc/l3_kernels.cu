@@ -536,7 +536,6 @@ __device__ __forceinline__ void imdct_short_band(const typename VT<NCH>::T* x, t
     for (int i = 0; i < 6; i++) ovl[i] = nd[i];
 }
 
-constexpr int kDRows = 33;    // 15 history rows + 18 rows of the current granule
 constexpr int kDStride = 33;  // T elements per row (odd: the DCT's per-slot column writes hit distinct banks)
 constexpr int kMaxIter = kTileGranules + 2;
 
@@ -1059,7 +1058,8 @@ void launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_s
                     uint32_t n_mono, cudaStream_t s, cudaEvent_t ev_mid) {
     static const int warps_env = getenv("L3B_GRANULE_WARPS") ? atoi(getenv("L3B_GRANULE_WARPS")) : kGranuleWarpsStereo;
     if (warps_env == 8) launch_granule_t<2, 8>(p, tiles_stereo, n_stereo, s);
-    else if (warps_env == 4) launch_granule_t<2, 4>(p, tiles_stereo, n_stereo, s);
+    else if (warps_env == 16) launch_granule_t<2, 16>(p, tiles_stereo, n_stereo, s);
+    else if (warps_env == 2) launch_granule_t<2, 2>(p, tiles_stereo, n_stereo, s);
     else launch_granule_t<2, kGranuleWarpsStereo>(p, tiles_stereo, n_stereo, s);
     if (ev_mid) cudaEventRecord(ev_mid, s);
     launch_granule_t<1, kGranuleWarpsMono>(p, tiles_mono, n_mono, s);

@@ -57,8 +57,8 @@ struct BatchParams {
     DeviceTables t;
 };
 
-constexpr int kGranuleWarpsStereo = 16;  // warps (= tiles) per CTA of the granule kernel, one CTA per SM
-constexpr int kGranuleWarpsMono = 16;
+constexpr int kGranuleWarpsStereo = 4;   // warps (= tiles) per CTA of the granule kernel; 16 warps resident per SM.
+constexpr int kGranuleWarpsMono = 4;     // 4-warp CTAs measured best (16: 33.7 ms, 8: 28.6 ms, 4: 27.2 ms on config 2)
 
 __global__ void l3_entropy_kernel(BatchParams p);
 template <int NCH, int WARPS>

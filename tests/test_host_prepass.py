@@ -1,0 +1,98 @@
+"""Host prepass (frame sync, side info, reservoir slicing) against the oracle's control flow (CPU only):
+which frames decode, how many samples are delivered, stream properties -- including damaged input."""
+from dataclasses import replace
+
+import numpy as np
+import pytest
+
+
+def scan_vs_oracle(data, label=""):
+    import audio_formats_b200 as af
+    import oracle
+    try:
+        ref = oracle.OracleStream(data)
+    except ValueError:
+        with pytest.raises(af.L3BError):
+            af.Scan(data)
+        return None
+    sc = af.Scan(data)
+    assert (sc.channels, sc.samplerate, sc.length_frames) == (ref.channels, ref.samplerate, ref.length_frames), label
+    ref.close()
+    pcm, taps = oracle.decode_all(data, taps=1 << 14)
+    assert sc.delivered_samples == pcm.size, label
+    return sc, pcm, taps
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c3", "c5"] + [f"c4_{i}" for i in range(12)])
+def test_clean_streams(built, cfg):
+    from audio_formats_b200 import synth
+    p = {"c1": synth.config1_params(1), "c3": synth.config3_params(3, 4.0), "c5": synth.config5_params(5, 4.0)}.get(cfg)
+    if p is None:
+        p = synth.config4_params(int(cfg.split("_")[1]), 3.0)
+    st = synth.generate(p)
+    sc, pcm, taps = scan_vs_oracle(st.data, cfg)
+    assert sc.granules == len(taps) == st.granules
+    d = sc.descs.reshape(sc.granules, sc.channels)
+    assert (d["w3"][0] >> 31).all() and not (d["w3"][1:] >> 31).any()   # state is zero only before the first granule
+    assert (np.diff(d["bit_start"].reshape(-1).astype(np.int64)) >= 0).all()   # bit offsets grow monotonically
+
+
+def test_tags_and_crc(built):
+    from audio_formats_b200 import synth
+    p = replace(synth.config3_params(12, 2.0), crc=1, id3v2_bytes=4096, id3v1=1)
+    scan_vs_oracle(synth.generate(p).data, "tags")
+
+
+def test_first_frames_without_reservoir_are_skipped(built):
+    """Cutting the head off a stream leaves frames whose main_data_begin points before the cut: they emit no PCM
+    and do not count in the length (minimp3.d:1546-1556, minimp3_ex.d:613-619)."""
+    from audio_formats_b200 import synth
+    from audio_formats_b200.api import Scan
+    st = synth.generate(replace(synth.config1_params(3), reservoir=2, nframes=60))
+    whole = Scan(st.data)
+    # cut at the start of frame 5 (frames are 417/418 bytes at 44.1 kHz / 128 kbps)
+    import oracle
+    L = oracle.lib()
+    pos, k = 0, 0
+    b = st.data
+    while k < 5:
+        pos += L.l3o_hdr_frame_bytes(b[pos:pos + 4], 0) + L.l3o_hdr_padding(b[pos:pos + 4])
+        k += 1
+    cut = b[pos:]
+    res = scan_vs_oracle(cut, "cut")
+    assert res is not None
+    sc, pcm, taps = res
+    assert sc.granules < whole.granules - 2 * 5 + 1   # at least one more frame lost to the missing reservoir
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fault_injection(built, seed):
+    """Truncation, garbage, corrupted side info: the prepass must follow the oracle's resync/drop decisions."""
+    from audio_formats_b200 import synth
+    rng = np.random.default_rng(seed)
+    st = synth.generate(replace(synth.config3_params(100 + seed, 1.5), nframes=50))
+    b = bytearray(st.data)
+    kind = seed % 5
+    if kind == 0:      # truncate mid-frame
+        b = b[: len(b) - int(rng.integers(1, 400))]
+    elif kind == 1:    # garbage prefix
+        b = bytearray(rng.integers(0, 255, 777, dtype=np.uint8).tobytes()) + b
+    elif kind == 2:    # overwrite a run of bytes in the middle (kills headers and side info)
+        at = len(b) // 2
+        b[at:at + 900] = rng.integers(0, 256, 900, dtype=np.uint8).tobytes()
+    elif kind == 3:    # flip bits in side infos of several frames
+        for _ in range(6):
+            at = int(rng.integers(0, len(b) - 40))
+            b[at] ^= 1 << int(rng.integers(0, 8))
+    else:              # drop a whole chunk (lost sync)
+        at = len(b) // 3
+        del b[at:at + 1000]
+    scan_vs_oracle(bytes(b), f"fault{kind}")
+
+
+def test_not_mp3(built):
+    import audio_formats_b200 as af
+    with pytest.raises(af.L3BError):
+        af.Scan(b"RIFF" + bytes(5000))
+    with pytest.raises(af.L3BError):
+        af.Scan(b"")
