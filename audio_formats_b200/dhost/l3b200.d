@@ -1,0 +1,119 @@
+/**
+  extern(C) bindings of include/l3b200.h (the CUDA shim + host layer of libl3b200.so).
+
+  NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no D compiler (dmd/ldc2/gdc/dub absent).
+  tests/test_dhost_bindings.py checks that every function declared in the C header is declared here
+  with the same name, so the two cannot drift silently.
+*/
+module audioformats.l3b200;
+
+nothrow @nogc extern(C):
+
+enum L3B_OK = 0;
+enum L3B_E_PARAM = -1;       // MP3D_E_PARAM   minimp3_ex.d:30
+enum L3B_E_MEMORY = -2;      // MP3D_E_MEMORY  minimp3_ex.d:31
+enum L3B_E_IOERROR = -3;     // MP3D_E_IOERROR minimp3_ex.d:32
+enum L3B_E_USER = -4;        // MP3D_E_USER    minimp3_ex.d:33
+enum L3B_E_DECODE = -5;      // MP3D_E_DECODE  minimp3_ex.d:34
+enum L3B_E_NOGPU = -16;
+enum L3B_E_UNSUPPORTED = -17;
+
+struct l3b_grch_desc_t
+{
+    uint bit_start;
+    uint w1;
+    uint w2;
+    uint w3;
+}
+
+struct l3b_stream_desc_t
+{
+    ulong maindata_off;
+    uint maindata_bytes;
+    uint n_granules;
+    ulong first_grch;
+    ulong pcm_off;
+    ulong pcm_skip;
+    ulong pcm_count;
+    ubyte nch;
+    ubyte sr_idx;
+    ubyte mpeg1;
+    ubyte reserved;
+    uint reserved2;
+}
+
+struct l3b_taps_t
+{
+    short* is_;
+    ubyte* iscf;
+    ubyte* ist_pos;
+}
+
+struct l3b_batch_t
+{
+    const(ubyte)* maindata;
+    ulong maindata_bytes;
+    const(l3b_grch_desc_t)* grch;
+    ulong n_grch;
+    const(l3b_stream_desc_t)* streams;
+    uint n_streams;
+    float* pcm;
+    ulong pcm_floats;
+    int* status;
+    const(l3b_taps_t)* taps;
+}
+
+struct l3b_ctx;
+struct l3b_resident;
+struct l3b_scan;
+struct l3b_stream;
+alias l3b_ctx_t = l3b_ctx;
+alias l3b_resident_t = l3b_resident;
+alias l3b_scan_t = l3b_scan;
+alias l3b_stream_t = l3b_stream;
+
+// layer 1: shim
+int l3b_device_count();
+int l3b_ctx_create(int device_id, l3b_ctx_t** outCtx);
+void l3b_ctx_destroy(l3b_ctx_t* ctx);
+const(char)* l3b_last_error(const(l3b_ctx_t)* ctx);
+int l3b_decode_batch(l3b_ctx_t* ctx, const(l3b_batch_t)* batch);
+int l3b_batch_upload(l3b_ctx_t* ctx, const(l3b_batch_t)* batch, l3b_resident_t** outResident);
+int l3b_batch_reupload(l3b_ctx_t* ctx, l3b_resident_t* r, const(l3b_batch_t)* batch);
+int l3b_batch_run(l3b_ctx_t* ctx, l3b_resident_t* r);
+int l3b_batch_sync(l3b_ctx_t* ctx);
+int l3b_batch_download(l3b_ctx_t* ctx, l3b_resident_t* r, float* pcm_host, ulong first_float, ulong n_floats);
+int l3b_batch_download_taps(l3b_ctx_t* ctx, l3b_resident_t* r, const(l3b_taps_t)* taps);
+void* l3b_batch_device_pcm(l3b_resident_t* r);
+void l3b_batch_free(l3b_ctx_t* ctx, l3b_resident_t* r);
+int l3b_batch_timing(l3b_ctx_t* ctx, int last_runs, float* ms3, int* launches);
+void* l3b_ctx_cuda_stream(l3b_ctx_t* ctx);
+
+// layer 2: host prepass + AudioStream surface as implemented in C++ (the D host below can use either its own
+// prepass, mp3host.d, or these)
+int l3b_scan_memory(const(ubyte)* data, size_t size, l3b_scan_t** outScan);
+void l3b_scan_free(l3b_scan_t* s);
+int l3b_scan_channels(const(l3b_scan_t)* s);
+int l3b_scan_samplerate(const(l3b_scan_t)* s);
+int l3b_scan_error(const(l3b_scan_t)* s);
+ulong l3b_scan_length_frames(const(l3b_scan_t)* s);
+ulong l3b_scan_delivered_samples(const(l3b_scan_t)* s);
+uint l3b_scan_granules(const(l3b_scan_t)* s);
+ulong l3b_scan_maindata_bytes(const(l3b_scan_t)* s);
+const(ubyte)* l3b_scan_maindata(const(l3b_scan_t)* s);
+const(l3b_grch_desc_t)* l3b_scan_descs(const(l3b_scan_t)* s);
+void l3b_scan_fill_stream_desc(const(l3b_scan_t)* s, l3b_stream_desc_t* outDesc);
+int l3b_decode_scans(l3b_ctx_t* ctx, l3b_scan_t** scans, uint n, float** pcm, int* status);
+
+int l3b_stream_open_memory(l3b_ctx_t* ctx, const(ubyte)* data, size_t size, l3b_stream_t** outStream);
+int l3b_stream_open_file(l3b_ctx_t* ctx, const(char)* path, l3b_stream_t** outStream);
+void l3b_stream_close(l3b_stream_t* s);
+int l3b_stream_num_channels(const(l3b_stream_t)* s);
+long l3b_stream_length_frames(const(l3b_stream_t)* s);
+float l3b_stream_samplerate(const(l3b_stream_t)* s);
+int l3b_stream_read_float(l3b_stream_t* s, float* outData, int frames);
+int l3b_stream_read_double(l3b_stream_t* s, double* outData, int frames);
+int l3b_stream_seek(l3b_stream_t* s, int frame);
+int l3b_stream_tell(const(l3b_stream_t)* s);
+int l3b_stream_is_error(const(l3b_stream_t)* s);
+const(char)* l3b_stream_error_message(const(l3b_stream_t)* s);
