@@ -7,3 +7,4 @@ There is no CPU fallback: every compute call raises when the library or a CUDA d
 """
 from .api import (AudioStream, Context, L3BError, Scan, decode_batch_with_taps, device_count, library_path,  # noqa: F401
                   load_library)
+from .pipeline import BatchPipeline  # noqa: F401

@@ -14,7 +14,10 @@ from typing import Sequence
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-_LIB_PATH = _HERE / "libl3b200.so"
+import os as _os
+
+# L3B_LIB selects an experimental build of the library (tools/, profiling); the product is libl3b200.so
+_LIB_PATH = Path(_os.environ["L3B_LIB"]) if _os.environ.get("L3B_LIB") else _HERE / "libl3b200.so"
 _lib = None
 
 
@@ -76,8 +79,11 @@ def load_library():
         "l3b_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
         "l3b_ctx_destroy": (None, [vp]),
         "l3b_last_error": (C.c_char_p, [vp]),
+        "l3b_host_alloc": (vp, [C.c_size_t]),
+        "l3b_host_free": (None, [vp]),
         "l3b_decode_batch": (C.c_int, [vp, C.POINTER(Batch)]),
         "l3b_batch_upload": (C.c_int, [vp, C.POINTER(Batch), C.POINTER(vp)]),
+        "l3b_batch_upload_reuse": (C.c_int, [vp, C.POINTER(Batch), C.POINTER(vp)]),
         "l3b_batch_reupload": (C.c_int, [vp, vp, C.POINTER(Batch)]),
         "l3b_batch_run": (C.c_int, [vp, vp]),
         "l3b_batch_sync": (C.c_int, [vp]),
@@ -219,10 +225,39 @@ class Context:
         return ResidentBatch(self, h, batch)
 
 
-class HostBatch:
-    """A batch assembled on the host from scans (what the D host hands to the shim)."""
+class PinnedBuffer:
+    """Page-locked host memory (cudaHostAlloc) viewed as a numpy array."""
 
-    def __init__(self, scans: Sequence[Scan], want_taps: bool = False, replicate: int = 1):
+    def __init__(self, nbytes: int):
+        self._L = load_library()
+        self.nbytes = int(nbytes)
+        self.ptr = self._L.l3b_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise L3BError(E_MEMORY, f"cannot pin {nbytes} bytes of host memory")
+        self.u8 = np.frombuffer((C.c_uint8 * self.nbytes).from_address(self.ptr), dtype=np.uint8)
+
+    def view(self, dtype, count=None):
+        a = self.u8.view(dtype)
+        return a if count is None else a[:count]
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.u8 = None
+            self._L.l3b_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class HostBatch:
+    """A batch assembled on the host from scans (what the D host hands to the shim).
+    `staging` (optional PinnedBuffer) receives the blob and the descriptors so the H2D copies read pinned memory."""
+
+    def __init__(self, scans: Sequence[Scan], want_taps: bool = False, replicate: int = 1, staging: "PinnedBuffer | None" = None):
         self.scans = list(scans)
         self.want_taps = want_taps
         blobs, descs = [], []
@@ -233,6 +268,7 @@ class HostBatch:
         for _ in range(replicate):
             for (md, ds, d0) in cache:
                 pad = (-len(md)) % 16 + 16
+                pcm = (pcm + 3) & ~3   # 16-byte aligned PCM rows (stereo stores are 8-byte vectors)
                 sd[k] = (off, len(md), d0.n_granules, grch, pcm, d0.pcm_skip, d0.pcm_count, d0.nch, d0.sr_idx, d0.mpeg1, 0, 0)
                 blobs.append(md)
                 blobs.append(np.zeros(pad, np.uint8))
@@ -241,8 +277,16 @@ class HostBatch:
                 grch += len(ds)
                 pcm += d0.pcm_count
                 k += 1
-        self.blob = np.concatenate(blobs) if blobs else np.zeros(0, np.uint8)
-        self.descs = np.concatenate(descs) if descs else np.zeros(0, GRCH_DTYPE)
+        n_desc = sum(len(d) for d in descs)
+        if staging is not None and off + 16 * n_desc + 64 <= staging.nbytes:
+            self.blob = staging.u8[:off]
+            np.concatenate(blobs, out=self.blob) if blobs else None
+            doff = (off + 63) & ~63
+            self.descs = staging.u8[doff:doff + 16 * n_desc].view(GRCH_DTYPE)
+            np.concatenate(descs, out=self.descs) if descs else None
+        else:
+            self.blob = np.concatenate(blobs) if blobs else np.zeros(0, np.uint8)
+            self.descs = np.concatenate(descs) if descs else np.zeros(0, GRCH_DTYPE)
         self.streams = sd
         self.pcm_floats = int(pcm)
         self.n_grch = int(grch)
@@ -327,11 +371,10 @@ def decode_batch_with_taps(ctx: Context, scans: Sequence[Scan]):
         taps = rb.download_taps()
     finally:
         rb.free()
-    outs, off = [], 0
+    outs = []
     for s, sdesc in zip(scans, hb.streams):
-        n = int(sdesc["pcm_count"])
+        off, n = int(sdesc["pcm_off"]), int(sdesc["pcm_count"])
         outs.append(pcm[off:off + n].reshape(-1, s.channels))
-        off += n
     return outs, *taps
 
 

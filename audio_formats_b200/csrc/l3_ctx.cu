@@ -40,6 +40,9 @@ struct l3b_resident {
     uint32_t n_tiles[2] = {0, 0};
     uint64_t n_grch = 0, pcm_floats = 0;
     uint32_t n_streams = 0;
+    // capacities of the device buffers (elements), for l3b_batch_upload_reuse
+    uint64_t cap_blob = 0, cap_grch = 0, cap_pcm = 0;
+    uint32_t cap_streams = 0, cap_tiles[2] = {0, 0};
     BatchParams params{};
 };
 
@@ -138,6 +141,16 @@ void l3b_ctx_destroy(l3b_ctx_t* c) {
 
 void* l3b_ctx_cuda_stream(l3b_ctx_t* c) { return c ? (void*)c->stream : nullptr; }
 
+void* l3b_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void l3b_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 void l3b_batch_free(l3b_ctx_t* c, l3b_resident_t* r) {
     if (!r) return;
     if (c) cudaSetDevice(c->device);
@@ -152,9 +165,9 @@ void l3b_batch_free(l3b_ctx_t* c, l3b_resident_t* r) {
     delete r;
 }
 
-int l3b_batch_upload(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** out) {
-    if (!c || !b || !out) return L3B_E_PARAM;
-    *out = nullptr;
+static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inout, bool reuse) {
+    if (!c || !b || !inout) return L3B_E_PARAM;
+    if (!reuse) *inout = nullptr;
     if (!b->n_streams || !b->streams || (b->n_grch && !b->grch) || (b->maindata_bytes && !b->maindata)) {
         c->err = "empty or inconsistent batch";
         return L3B_E_PARAM;
@@ -167,7 +180,8 @@ int l3b_batch_upload(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** out) {
         const l3b_stream_desc_t& s = b->streams[i];
         if ((s.nch != 1 && s.nch != 2) || s.sr_idx > 7 || (s.maindata_off & 3) ||
             s.maindata_off + s.maindata_bytes > b->maindata_bytes || s.first_grch != expect_grch ||
-            s.pcm_off + s.pcm_count > b->pcm_floats || s.pcm_skip + s.pcm_count > (uint64_t)s.n_granules * 576u * s.nch) {
+            s.pcm_off + s.pcm_count > b->pcm_floats || s.pcm_skip + s.pcm_count > (uint64_t)s.n_granules * 576u * s.nch ||
+            (s.nch == 2 && ((s.pcm_off | s.pcm_skip | s.pcm_count) & 1))) {
             c->err = "stream descriptor " + std::to_string(i) + " is inconsistent";
             return L3B_E_PARAM;
         }
@@ -181,12 +195,12 @@ int l3b_batch_upload(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** out) {
     if (expect_grch != b->n_grch) { c->err = "n_grch does not match the stream table"; return L3B_E_PARAM; }
 
     CU_TRY(c, cudaSetDevice(c->device));
-    l3b_resident* r = new (std::nothrow) l3b_resident();
-    if (!r) return L3B_E_MEMORY;
-    r->n_grch = b->n_grch;
-    r->n_streams = b->n_streams;
-    r->pcm_floats = b->pcm_floats;
-    auto bail = [&](int code) { l3b_batch_free(c, r); return code; };
+    l3b_resident* r = *inout;
+    if (!r) {
+        r = new (std::nothrow) l3b_resident();
+        if (!r) return L3B_E_MEMORY;
+    }
+    auto bail = [&](int code) { l3b_batch_free(c, r); *inout = nullptr; return code; };
 #define CU_TRY_R(expr)                                                                        \
     do {                                                                                      \
         cudaError_t e_ = (expr);                                                              \
@@ -195,24 +209,55 @@ int l3b_batch_upload(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** out) {
             return bail(e_ == cudaErrorMemoryAllocation ? L3B_E_MEMORY : L3B_E_NOGPU);        \
         }                                                                                     \
     } while (0)
-    const size_t blob_alloc = (size_t)b->maindata_bytes + 64;
-    CU_TRY_R(cudaMalloc(&r->d_blob, blob_alloc));
-    CU_TRY_R(cudaMemsetAsync(r->d_blob + b->maindata_bytes, 0, 64, c->stream));
-    if (b->maindata_bytes) CU_TRY_R(cudaMemcpyAsync(r->d_blob, b->maindata, b->maindata_bytes, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY_R(cudaMalloc(&r->d_grch, std::max<size_t>(16, b->n_grch * sizeof(l3b_grch_desc_t))));
-    if (b->n_grch) CU_TRY_R(cudaMemcpyAsync(r->d_grch, b->grch, b->n_grch * sizeof(l3b_grch_desc_t), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY_R(cudaMalloc(&r->d_streams, b->n_streams * sizeof(l3b_stream_desc_t)));
-    CU_TRY_R(cudaMemcpyAsync(r->d_streams, b->streams, b->n_streams * sizeof(l3b_stream_desc_t), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY_R(cudaMalloc(&r->d_is, std::max<size_t>(16, b->n_grch * kIsChunks * sizeof(uint4))));
-    CU_TRY_R(cudaMalloc(&r->d_sf, std::max<size_t>(16, b->n_grch * kSfRecBytes)));
-    CU_TRY_R(cudaMalloc(&r->d_pcm, std::max<size_t>(16, b->pcm_floats * sizeof(float))));
+    // (re)allocate what is too small; recycled workspaces get 12.5 % headroom so that they settle quickly
+    auto grow = [&](uint64_t need) { return reuse ? need + need / 8 + 64 : need; };
+    bool stale = false;  // a buffer in use by queued work is about to be freed
+    if (b->maindata_bytes + 64 > r->cap_blob || b->n_grch > r->cap_grch || b->pcm_floats > r->cap_pcm ||
+        b->n_streams > r->cap_streams || tiles[0].size() > r->cap_tiles[0] || tiles[1].size() > r->cap_tiles[1])
+        stale = true;
+    if (stale && r->cap_blob) CU_TRY_R(cudaStreamSynchronize(c->stream));
+    if (b->maindata_bytes + 64 > r->cap_blob) {
+        cudaFree(r->d_blob); r->d_blob = nullptr;
+        r->cap_blob = grow(b->maindata_bytes + 64);
+        CU_TRY_R(cudaMalloc(&r->d_blob, r->cap_blob));
+    }
+    if (b->n_grch > r->cap_grch || !r->d_grch) {
+        cudaFree(r->d_grch); cudaFree(r->d_is); cudaFree(r->d_sf);
+        r->d_grch = nullptr; r->d_is = nullptr; r->d_sf = nullptr;
+        r->cap_grch = std::max<uint64_t>(1, grow(b->n_grch));
+        CU_TRY_R(cudaMalloc(&r->d_grch, r->cap_grch * sizeof(l3b_grch_desc_t)));
+        CU_TRY_R(cudaMalloc(&r->d_is, r->cap_grch * kIsChunks * sizeof(uint4)));
+        CU_TRY_R(cudaMalloc(&r->d_sf, r->cap_grch * kSfRecBytes));
+    }
+    if (b->pcm_floats > r->cap_pcm || !r->d_pcm) {
+        cudaFree(r->d_pcm); r->d_pcm = nullptr;
+        r->cap_pcm = std::max<uint64_t>(4, grow(b->pcm_floats));
+        CU_TRY_R(cudaMalloc(&r->d_pcm, r->cap_pcm * sizeof(float)));
+    }
+    if (b->n_streams > r->cap_streams) {
+        cudaFree(r->d_streams); r->d_streams = nullptr;
+        r->cap_streams = (uint32_t)grow(b->n_streams);
+        CU_TRY_R(cudaMalloc(&r->d_streams, r->cap_streams * sizeof(l3b_stream_desc_t)));
+    }
     for (int k = 0; k < 2; k++) {
         r->n_tiles[k] = (uint32_t)tiles[k].size();
-        if (!r->n_tiles[k]) continue;
-        CU_TRY_R(cudaMalloc(&r->d_tiles[k], tiles[k].size() * sizeof(Tile)));
-        CU_TRY_R(cudaMemcpyAsync(r->d_tiles[k], tiles[k].data(), tiles[k].size() * sizeof(Tile), cudaMemcpyHostToDevice, c->stream));
+        if (tiles[k].size() > r->cap_tiles[k]) {
+            cudaFree(r->d_tiles[k]); r->d_tiles[k] = nullptr;
+            r->cap_tiles[k] = (uint32_t)grow(tiles[k].size());
+            CU_TRY_R(cudaMalloc(&r->d_tiles[k], r->cap_tiles[k] * sizeof(Tile)));
+        }
     }
-    CU_TRY_R(cudaStreamSynchronize(c->stream));  // host vectors above go out of scope
+    r->n_grch = b->n_grch;
+    r->n_streams = b->n_streams;
+    r->pcm_floats = b->pcm_floats;
+    CU_TRY_R(cudaMemsetAsync(r->d_blob + b->maindata_bytes, 0, 64, c->stream));
+    if (b->maindata_bytes) CU_TRY_R(cudaMemcpyAsync(r->d_blob, b->maindata, b->maindata_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (b->n_grch) CU_TRY_R(cudaMemcpyAsync(r->d_grch, b->grch, b->n_grch * sizeof(l3b_grch_desc_t), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY_R(cudaMemcpyAsync(r->d_streams, b->streams, b->n_streams * sizeof(l3b_stream_desc_t), cudaMemcpyHostToDevice, c->stream));
+    for (int k = 0; k < 2; k++)
+        if (r->n_tiles[k])
+            CU_TRY_R(cudaMemcpyAsync(r->d_tiles[k], tiles[k].data(), tiles[k].size() * sizeof(Tile), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY_R(cudaStreamSynchronize(c->stream));  // the host tile vectors go out of scope
 #undef CU_TRY_R
     BatchParams& p = r->params;
     p.blob = r->d_blob;
@@ -225,9 +270,12 @@ int l3b_batch_upload(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** out) {
     p.pcm = r->d_pcm;
     p.zero_fill = b->taps ? 1 : 0;
     p.t = c->t;
-    *out = r;
+    *inout = r;
     return 0;
 }
+
+int l3b_batch_upload(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** out) { return upload_impl(c, b, out, false); }
+int l3b_batch_upload_reuse(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inout) { return upload_impl(c, b, inout, true); }
 
 int l3b_batch_reupload(l3b_ctx_t* c, l3b_resident_t* r, const l3b_batch_t* b) {
     if (!c || !r || !b) return L3B_E_PARAM;
@@ -351,6 +399,7 @@ int l3b_decode_scans(l3b_ctx_t* c, l3b_scan_t* const* scans, uint32_t n, float* 
         l3b_scan_fill_stream_desc(scans[i], &sd[i]);
         sd[i].maindata_off = blob.size();
         sd[i].first_grch = descs.size();
+        pcm_total = (pcm_total + 3) & ~(uint64_t)3;  // 16-byte aligned PCM rows (stereo stores are 8-byte vectors)
         sd[i].pcm_off = pcm_total;
         pcm_total += s.pcm_count;
         blob.insert(blob.end(), s.prog.blob.begin(), s.prog.blob.end());

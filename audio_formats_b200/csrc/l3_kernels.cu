@@ -355,6 +355,12 @@ __global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
 //   window                  lane = (slot parity, inner index i of minimp3.d:1371), 16-tap sliding register window
 // Shared memory per warp: spectrum T[608], DCT history T[33 rows x 33], small tables.  No block barriers.
 
+#ifdef L3B_EXP_NO_PHASE_SYNC
+#define L3B_PHASE_SYNC() ((void)0)
+#else
+#define L3B_PHASE_SYNC() __syncthreads()
+#endif
+
 template <int NCH> struct VT;
 template <> struct VT<1> {
     typedef float T;
@@ -375,10 +381,23 @@ template <> struct VT<2> {
     typedef float2 T;
     static __device__ __forceinline__ T zero() { return make_float2(0.0f, 0.0f); }
     static __device__ __forceinline__ T neg(T a) { return make_float2(-a.x, -a.y); }
+#ifdef L3B_EXP_PACKED_MUL
+    // EXPERIMENT ONLY: packed multiplies + FADD2.FTZ (the ftz mismatch stops ptxas from contracting them into
+    // FFMA2); results below 1.18e-38 flush to zero, so this is NOT the bit-exact configuration.
+    static __device__ __forceinline__ T add(T a, T b) {
+        unsigned long long r, x = *reinterpret_cast<unsigned long long*>(&a), y = *reinterpret_cast<unsigned long long*>(&b);
+        asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+        return *reinterpret_cast<float2*>(&r);
+    }
+    static __device__ __forceinline__ T sub(T a, T b) { return add(a, neg(b)); }
+    static __device__ __forceinline__ T mul(T a, T b) { return __fmul2_rn(a, b); }
+    static __device__ __forceinline__ T muls(T a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+#else
     static __device__ __forceinline__ T add(T a, T b) { return __fadd2_rn(a, b); }
     static __device__ __forceinline__ T sub(T a, T b) { return __fadd2_rn(a, neg(b)); }
     static __device__ __forceinline__ T mul(T a, T b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
     static __device__ __forceinline__ T muls(T a, float s) { return make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s)); }
+#endif
     static __device__ __forceinline__ T mulw(T a, float w0, float w1) { return make_float2(__fmul_rn(a.x, w0), __fmul_rn(a.y, w1)); }
     static __device__ __forceinline__ T shfl_up(T a) {
         return make_float2(__shfl_up_sync(0xffffffffu, a.x, 1), __shfl_up_sync(0xffffffffu, a.y, 1));
@@ -823,7 +842,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 __syncwarp();
             }
         }
-        __syncthreads();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
+        L3B_PHASE_SYNC();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
 
         // ---------------- reorder + antialias + IMDCT + frequency inversion (minimp3.d:1215-1229) ----------
         if (act) {
@@ -884,7 +903,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 for (int i = 0; i < 18; i++) xr[lane * 19 + i] = y[i];
             }
         }
-        __syncthreads();
+        L3B_PHASE_SYNC();
 
         // ---------------- DCT-32 matrixing across bands, one time slot per lane (minimp3.d:1232-1298) -------
         if (act && mode >= 1 && lane < 18) {
@@ -944,7 +963,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             out[30] = t[1][7];
             out[31] = t[3][7];
         }
-        __syncthreads();
+        L3B_PHASE_SYNC();
 
         // ---------------- 512-tap window (minimp3.d:1305-1406) ----------------
         if (act && mode == 2) {

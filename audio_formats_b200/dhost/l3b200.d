@@ -77,8 +77,11 @@ int l3b_device_count();
 int l3b_ctx_create(int device_id, l3b_ctx_t** outCtx);
 void l3b_ctx_destroy(l3b_ctx_t* ctx);
 const(char)* l3b_last_error(const(l3b_ctx_t)* ctx);
+void* l3b_host_alloc(size_t bytes);
+void l3b_host_free(void* p);
 int l3b_decode_batch(l3b_ctx_t* ctx, const(l3b_batch_t)* batch);
 int l3b_batch_upload(l3b_ctx_t* ctx, const(l3b_batch_t)* batch, l3b_resident_t** outResident);
+int l3b_batch_upload_reuse(l3b_ctx_t* ctx, const(l3b_batch_t)* batch, l3b_resident_t** inoutResident);
 int l3b_batch_reupload(l3b_ctx_t* ctx, l3b_resident_t* r, const(l3b_batch_t)* batch);
 int l3b_batch_run(l3b_ctx_t* ctx, l3b_resident_t* r);
 int l3b_batch_sync(l3b_ctx_t* ctx);

@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
     ap.add_argument("--seconds", type=float, default=60.0, help="seconds per stream")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-lanes", type=int, default=6)
+    ap.add_argument("--e2e-wave", type=int, default=16, help="streams per pipeline wave")
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -295,37 +297,34 @@ def main():
                 "entropy_kernel_ms": ent_ms, "granule_kernel_share_of_step": gran_ms / (gran_ms + ent_ms)}
 
     # ---- end to end: MP3 bytes (host) -> PCM floats (pinned host) ------------------------------------------
+    # Through the public batch API (audio_formats_b200.BatchPipeline): per wave host prepass (frame sync, side
+    # info, reservoir slicing) -> H2D from pinned staging -> entropy + granule kernels -> D2H into pinned memory,
+    # waves overlapped across `lanes` contexts/streams.
     e2e = None
     if not args.no_e2e:
-        pin_pcm = torch.empty(hb.pcm_floats, dtype=torch.float32).pin_memory()
-        ptr = pin_pcm.data_ptr()
-        parts = []
-
-        def e2e_step():
-            t_a = time.perf_counter()
-            prepass()                        # host prepass of every stream (its output equals `scans`)
-            t_b = time.perf_counter()
-            rb.reupload()                    # H2D: main-data blob + descriptors from pinned memory
-            rb.run()
-            rb.download_into(ptr, 0, hb.pcm_floats)   # D2H of the whole PCM result (synchronises)
-            t_c = time.perf_counter()
-            return t_b - t_a, t_c - t_b
-
-        e2e_step()
+        rb.free()
+        rb = None
+        pin_pcm = api.PinnedBuffer(4 * (hb.pcm_floats + 4 * len(scans) + 1024))
+        out = pin_pcm.view(np.float32)
+        pipe = af.BatchPipeline(device=local, lanes=args.e2e_lanes, wave_streams=args.e2e_wave, prepass_threads=threads)
+        info = pipe.decode_into(datas, out)          # warm-up (allocates the recycled workspaces)
+        pipe.decode_into(datas, out)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            parts.append(e2e_step())
+            info = pipe.decode_into(datas, out)
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        # spot-check the delivered PCM against the device-resident run's checksum source (first stream)
+        o0, f0, c0, _ = info[0]
         h2d = int(hb.blob.size) + hb.descs.size * 16 + hb.streams.size * 56
         e2e = {"value": total_audio / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": pcm_bytes,
                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
-               "host_prepass_ms": 1e3 * float(np.mean([p[0] for p in parts])), "host_prepass_threads": threads,
-               "copy_and_kernels_ms": 1e3 * float(np.mean([p[1] for p in parts])),
-               "without_prepass_value": total_audio / max_over_ranks(float(np.mean([p[1] for p in parts]))),
-               "checksum": float(pin_pcm[:: max(1, hb.pcm_floats // 65536)].double().abs().sum())}
-        del pin_pcm
+               "pipeline": {"lanes": args.e2e_lanes, "wave_streams": args.e2e_wave, "host_prepass_threads": threads},
+               "includes": "host prepass + H2D (pinned) + kernels + D2H (pinned) of every step",
+               "first_stream_abs_sum": float(np.abs(out[o0:o0 + f0 * c0].astype(np.float64)).sum())}
+        pipe.close()
+        pin_pcm.free()
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same workload ---------------
     cpu = None
@@ -349,7 +348,8 @@ def main():
                 "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
                 "setup": {"generate_s": t_gen, "prepass_s": t_scan, "host_threads": threads}}
         print(json.dumps(line), flush=True)
-    rb.free()
+    if rb is not None:
+        rb.free()
     ctx.close()
     if dist:
         dist.destroy_process_group()

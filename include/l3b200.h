@@ -97,6 +97,11 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** out);
 void l3b_ctx_destroy(l3b_ctx_t* ctx);
 const char* l3b_last_error(const l3b_ctx_t* ctx); /* ctx may be NULL: last error of a failed create */
 
+/* Page-locked host memory for batch inputs / PCM outputs (cudaHostAlloc): copies from and to it run at full PCIe
+ * speed and asynchronously.  Returns NULL on failure. */
+void* l3b_host_alloc(size_t bytes);
+void l3b_host_free(void* p);
+
 /* Decode a whole batch, host buffers in / host buffers out (H2D + kernels + D2H inside). */
 int l3b_decode_batch(l3b_ctx_t* ctx, const l3b_batch_t* batch);
 
@@ -104,6 +109,9 @@ int l3b_decode_batch(l3b_ctx_t* ctx, const l3b_batch_t* batch);
  * l3b_batch_upload keeps descriptors + blob on the GPU and allocates the PCM buffer there. */
 typedef struct l3b_resident l3b_resident_t;
 int l3b_batch_upload(l3b_ctx_t* ctx, const l3b_batch_t* batch, l3b_resident_t** out);
+/* Like l3b_batch_upload, but recycles the device buffers of *inout when they are large enough (a steady-state
+ * pipeline decodes wave after wave through one workspace without cudaMalloc/cudaFree).  *inout may be NULL. */
+int l3b_batch_upload_reuse(l3b_ctx_t* ctx, const l3b_batch_t* batch, l3b_resident_t** inout);
 /* Refresh the inputs of an existing resident batch (same shape) from HOST memory: the per-step H2D of a
  * steady-state pipeline that reuses its device buffers. */
 int l3b_batch_reupload(l3b_ctx_t* ctx, l3b_resident_t* r, const l3b_batch_t* batch);
