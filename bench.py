@@ -285,8 +285,16 @@ def main():
     fp32_tflops = n_grch * FLOPS_PER_GRCH / (gran_ms * 1e-3) / 1e12
     hbm_ceiling = hbm_peak * 1e9 / (alg_bytes / audio_s)              # audio-s/s if HBM-bound
     fp32_ceiling = FP32_NOMINAL_TFLOPS * 1e12 / (n_grch * FLOPS_PER_GRCH / audio_s)
-    roofline = {"bound": "hbm", "kernel": "l3_granule_kernel<2>", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "peak_source": "measured" if peaks else "fallback", "traffic": None,
+    # DRAM traffic of the same kernel on the same workload, from one `ncu --set full` capture (profiles/r01_traffic.json);
+    # only quoted when this run IS that workload
+    traffic = None
+    tf = ROOT / "profiles" / "r01_traffic.json"
+    if tf.exists() and args.streams == 1024 and args.seconds == 60.0:
+        traffic = json.loads(tf.read_text()).get("granule", {}).get("traffic")
+    roofline = {"bound": "hbm", "kernel": "l3_granule_kernel<2,4>", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "peak_source": "measured" if peaks else "fallback", "traffic": traffic,
+                "traffic_note": "ncu dram read+write per launch; above the algorithmic bytes because the kernel reads the int16 "
+                                "spectra written by the entropy kernel (10.8 GB) and PCM sectors are written in two passes",
                 "ms_per_launch": gran_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "fp32": {"achieved_tflops": fp32_tflops, "peak_tflops_nominal": FP32_NOMINAL_TFLOPS,
                          "frac": fp32_tflops / FP32_NOMINAL_TFLOPS,
