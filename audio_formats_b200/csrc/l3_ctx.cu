@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -23,8 +24,12 @@ struct l3b_ctx {
     std::string err;
     void* d_tables = nullptr;  // one allocation holding every lookup table
     DeviceTables t{};
-    static constexpr int kRing = 64;  // runs whose per-kernel events are kept
-    cudaEvent_t ev[kRing * 4] = {};
+    cudaStream_t stream2 = nullptr;   // the granule kernels of a run go here, overlapping later entropy launches
+    static constexpr int kRing = 64;  // runs whose events are kept
+    static constexpr int kMaxSubs = 16;
+    // per run: [0] start, [1] last entropy launch done, [2] all done; then 2 per sub-batch around the granule launches
+    cudaEvent_t ev[kRing * (3 + 3 * kMaxSubs)] = {};
+    int subs_of_run[kRing] = {};
     uint64_t runs = 0;
     int last_launches = 0;
 };
@@ -43,6 +48,8 @@ struct l3b_resident {
     // capacities of the device buffers (elements), for l3b_batch_upload_reuse
     uint64_t cap_blob = 0, cap_grch = 0, cap_pcm = 0;
     uint32_t cap_streams = 0, cap_tiles[2] = {0, 0};
+    struct Sub { uint64_t grch_lo, grch_hi; uint32_t tile_lo[2], tile_hi[2]; };
+    std::vector<Sub> subs;   // the run is issued sub-batch by sub-batch (stream boundaries)
     BatchParams params{};
 };
 
@@ -86,9 +93,12 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** out) {
         return L3B_E_NOGPU;
     };
     if ((e = cudaSetDevice(device_id)) != cudaSuccess) return fail("cudaSetDevice", e);
-    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-    for (auto& ev : c->ev)
-        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // entropy launches get the higher priority: they fill idle slots
+        if ((e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, lo)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    }
 
     // lookup tables: one device allocation, sub-allocated at 256-byte granularity
     HuffLut hl = build_huff_lut();
@@ -136,6 +146,7 @@ void l3b_ctx_destroy(l3b_ctx_t* c) {
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     delete c;
 }
 
@@ -193,6 +204,28 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
             tiles[s.nch == 2 ? 0 : 1].push_back({i, g, std::min<uint32_t>(kTileGranules, g1 - g)});
     }
     if (expect_grch != b->n_grch) { c->err = "n_grch does not match the stream table"; return L3B_E_PARAM; }
+    // sub-batches: cut at stream boundaries into up to kMaxSubs pieces of similar size (>= 64 K granule-channels each)
+    std::vector<l3b_resident::Sub> subs;
+    {
+        int want = 1;  // measured on B200: overlapping the two kernels through sub-batches does not pay (39.2 ms for 1, 39.5 for 4, 41.3 for 16)
+        if (getenv("L3B_SUBBATCHES")) want = std::max(1, std::min((int)l3b_ctx::kMaxSubs, atoi(getenv("L3B_SUBBATCHES"))));
+        uint64_t per = (b->n_grch + want - 1) / want, lo = 0;
+        uint32_t t_at[2] = {0, 0};
+        l3b_resident::Sub cur{0, 0, {0, 0}, {0, 0}};
+        for (uint32_t i = 0; i < b->n_streams; i++) {
+            const l3b_stream_desc_t& s = b->streams[i];
+            uint64_t hi = s.first_grch + (uint64_t)s.n_granules * s.nch;
+            for (int k = 0; k < 2; k++)
+                while (t_at[k] < tiles[k].size() && tiles[k][t_at[k]].stream == i) t_at[k]++;
+            if (hi - lo >= per || i + 1 == b->n_streams) {
+                cur.grch_lo = lo; cur.grch_hi = hi;
+                cur.tile_hi[0] = t_at[0]; cur.tile_hi[1] = t_at[1];
+                subs.push_back(cur);
+                cur.tile_lo[0] = t_at[0]; cur.tile_lo[1] = t_at[1];
+                lo = hi;
+            }
+        }
+    }
 
     CU_TRY(c, cudaSetDevice(c->device));
     l3b_resident* r = *inout;
@@ -250,6 +283,7 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     r->n_grch = b->n_grch;
     r->n_streams = b->n_streams;
     r->pcm_floats = b->pcm_floats;
+    r->subs = subs;
     CU_TRY_R(cudaMemsetAsync(r->d_blob + b->maindata_bytes, 0, 64, c->stream));
     if (b->maindata_bytes) CU_TRY_R(cudaMemcpyAsync(r->d_blob, b->maindata, b->maindata_bytes, cudaMemcpyHostToDevice, c->stream));
     if (b->n_grch) CU_TRY_R(cudaMemcpyAsync(r->d_grch, b->grch, b->n_grch * sizeof(l3b_grch_desc_t), cudaMemcpyHostToDevice, c->stream));
@@ -290,17 +324,44 @@ int l3b_batch_reupload(l3b_ctx_t* c, l3b_resident_t* r, const l3b_batch_t* b) {
     return 0;
 }
 
+static cudaEvent_t* run_events(l3b_ctx* c, uint64_t run) {
+    cudaEvent_t* ev = c->ev + (run % l3b_ctx::kRing) * (3 + 3 * l3b_ctx::kMaxSubs);
+    if (!ev[0])
+        for (int i = 0; i < 3 + 3 * l3b_ctx::kMaxSubs; i++) cudaEventCreate(&ev[i]);
+    return ev;
+}
+
 int l3b_batch_run(l3b_ctx_t* c, l3b_resident_t* r) {
     if (!c || !r) return L3B_E_PARAM;
     CU_TRY(c, cudaSetDevice(c->device));
-    cudaEvent_t* ev = c->ev + 4 * (c->runs % l3b_ctx::kRing);
-    CU_TRY(c, cudaEventRecord(ev[0], c->stream));
-    launch_entropy(r->params, c->stream);
-    CU_TRY(c, cudaEventRecord(ev[1], c->stream));
-    launch_granule(r->params, r->d_tiles[0], r->n_tiles[0], r->d_tiles[1], r->n_tiles[1], c->stream, ev[2]);
-    CU_TRY(c, cudaEventRecord(ev[3], c->stream));
+    cudaEvent_t* ev = run_events(c, c->runs);
+    cudaStream_t A = c->stream, B = c->stream2;
+    const int ns = (int)r->subs.size();
+    CU_TRY(c, cudaEventRecord(ev[0], A));
+    CU_TRY(c, cudaStreamWaitEvent(B, ev[0], 0));   // uploads on A are complete before anything on B starts
+    int launches = 0;
+    for (int i = 0; i < ns; i++) {
+        const l3b_resident::Sub& sb = r->subs[i];
+        BatchParams p = r->params;
+        p.grch_lo = sb.grch_lo;
+        p.grch_hi = sb.grch_hi;
+        launch_entropy(p, A);
+        launches += sb.grch_hi > sb.grch_lo;
+        cudaEvent_t* se = ev + 3 + 3 * i;
+        CU_TRY(c, cudaEventRecord(se[0], A));
+        CU_TRY(c, cudaStreamWaitEvent(B, se[0], 0));   // granule kernels of sub-batch i wait for its spectra only
+        CU_TRY(c, cudaEventRecord(se[1], B));
+        const uint32_t n2 = sb.tile_hi[0] - sb.tile_lo[0], n1 = sb.tile_hi[1] - sb.tile_lo[1];
+        launch_granule(p, r->d_tiles[0] + sb.tile_lo[0], n2, r->d_tiles[1] + sb.tile_lo[1], n1, B, nullptr);
+        launches += (n2 > 0) + (n1 > 0);
+        CU_TRY(c, cudaEventRecord(se[2], B));
+    }
+    CU_TRY(c, cudaEventRecord(ev[1], A));
+    CU_TRY(c, cudaEventRecord(ev[2], B));
+    CU_TRY(c, cudaStreamWaitEvent(A, ev[2], 0));       // downloads / the next upload on A see finished PCM
     CU_TRY(c, cudaGetLastError());
-    c->last_launches = (r->n_grch ? 1 : 0) + (r->n_tiles[0] ? 1 : 0) + (r->n_tiles[1] ? 1 : 0);
+    c->subs_of_run[c->runs % l3b_ctx::kRing] = ns;
+    c->last_launches = launches;
     c->runs++;
     return 0;
 }
@@ -319,14 +380,20 @@ int l3b_batch_timing(l3b_ctx_t* c, int last_runs, float ms[3], int* launches) {
     if (last_runs > l3b_ctx::kRing) last_runs = l3b_ctx::kRing;
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream2));
     float sum[3] = {0, 0, 0};
     for (int k = 0; k < last_runs; k++) {
-        cudaEvent_t* ev = c->ev + 4 * ((c->runs - 1 - k) % l3b_ctx::kRing);
-        for (int i = 0; i < 3; i++) {
-            float t = 0;
-            CU_TRY(c, cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
-            sum[i] += t;
+        const uint64_t run = c->runs - 1 - k;
+        cudaEvent_t* ev = run_events(c, run);
+        float t = 0;
+        CU_TRY(c, cudaEventElapsedTime(&t, ev[0], ev[1]));   // entropy launches, first to last (stream A)
+        sum[0] += t;
+        for (int i = 0; i < c->subs_of_run[run % l3b_ctx::kRing]; i++) {
+            CU_TRY(c, cudaEventElapsedTime(&t, ev[3 + 3 * i + 1], ev[3 + 3 * i + 2]));   // granule launches of sub-batch i
+            sum[1] += t;
         }
+        CU_TRY(c, cudaEventElapsedTime(&t, ev[0], ev[2]));   // whole run
+        sum[2] += t;
     }
     if (ms) memcpy(ms, sum, sizeof sum);
     if (launches) *launches = c->last_launches * last_runs;

@@ -130,10 +130,10 @@ __global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
     for (uint32_t i = threadIdx.x; i < p.t.huff_entries; i += blockDim.x) s_lut[i] = p.t.huff[i];
     __syncthreads();
 
-    uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = gi < p.n_grch;
+    uint64_t gi = p.grch_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = gi < p.grch_hi;
     if (__all_sync(0xffffffffu, !live)) return;
-    if (!live) gi = p.n_grch - 1;  // tail lanes of the last warp shadow its last granule-channel in lockstep
+    if (!live) gi = p.grch_hi - 1;  // tail lanes of the last warp shadow its last granule-channel in lockstep
     const uint32_t si = find_stream(p.streams, p.n_streams, gi);
     const l3b_stream_desc_t* S = p.streams + si;
     const int nch = S->nch;
@@ -278,7 +278,6 @@ __global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
             reg = idx < r2 ? 1 : 2;
             cur = par[reg];
             nb = reg == 1 ? r2 : 576;
-            if (reg == 1 && idx >= r2) { cur = par[2]; nb = 576; }
         }
         const bool second = !in_big && (pend & 4u);
         const bool first = !in_big && !second;
@@ -288,35 +287,37 @@ __global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
         int w = (int)((pr >> 16) & 0xFF);
         uint32_t bits = L3_PEEK32();
         uint32_t e = s_lut[base + (bits >> (32 - w))];
-        while (e & 0x8000u) {  // codes longer than the root table (rare)
+        while (e & 0x8000u) {  // codes longer than the root table (rare): walk the sub-tables
             L3_ADVANCE(w);
             w = (int)((e >> 12) & 7) + 1;
             bits = L3_PEEK32();
             e = s_lut[base + (e & 0xFFFu) + (bits >> (32 - w))];
         }
-        L3_ADVANCE((e >> 8) & 15);
+        // `bits` is the 32-bit window at pos; the (rest of the) code is its top `len` bits, the sign bits follow
+        const int len = (int)((e >> 8) & 15);
         // quad bookkeeping: the limit is tested after the code and before the signs (minimp3.d:866), then the
         // sfb terminator before each half (minimp3.d:873, 876)
-        const bool stop = (first && pos > limit) || (!in_big && idx >= 576);
+        const bool stop = (first && pos + (uint32_t)len > limit) || (!in_big && idx >= 576);
         int a0 = second ? (int)(pend & 1u) : (int)(e & 15);
         int a1 = second ? (int)((pend >> 1) & 1u) : (int)((e >> 4) & 15);
         pend = first ? (4u | ((e >> 12) & 3u)) : 0u;
         done = done || stop;
         if (linbits && (a0 == 15 || a1 == 15)) {  // escapes (rare)
+            L3_ADVANCE(len);
             if (a0 == 15) { a0 += (int)(L3_PEEK32() >> (32 - linbits)); L3_ADVANCE(linbits); }
             { const int n0 = a0 != 0; const int sg = n0 & (int)(L3_PEEK32() >> 31); L3_ADVANCE(n0); a0 = sg ? -a0 : a0; }
             if (a1 == 15) { a1 += (int)(L3_PEEK32() >> (32 - linbits)); L3_ADVANCE(linbits); }
             { const int n1 = a1 != 0; const int sg = n1 & (int)(L3_PEEK32() >> 31); L3_ADVANCE(n1); a1 = sg ? -a1 : a1; }
         } else {
             const int n0 = a0 != 0, n1 = a1 != 0;
-            const uint32_t two = L3_PEEK32() >> 30;
-            const int s0 = n0 & (int)(two >> 1);
-            const int s1 = n1 & (int)(two >> (1 - n0));
-            L3_ADVANCE(n0 + n1);
+            const uint32_t sb = bits << len;            // sign bits at the top (len + 2 <= 32 always)
+            const int s0 = n0 & (int)(sb >> 31);
+            const int s1 = n1 & (int)((sb << n0) >> 31);
+            L3_ADVANCE(len + n0 + n1);                  // one advance for code + signs
             a0 = (a0 ^ -s0) + s0;
             a1 = (a1 ^ -s1) + s1;
         }
-        uint32_t pk = ((uint32_t)a0 & 0xFFFFu) | ((uint32_t)a1 << 16);
+        uint32_t pk = __byte_perm((uint32_t)a0, (uint32_t)a1, 0x5410);
         if (done) pk = 0; else idx += 2;
         return pk;
     };
@@ -1076,9 +1077,9 @@ static void launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n
 }
 
 void launch_entropy(const BatchParams& p, cudaStream_t s) {
-    if (!p.n_grch) return;
+    if (p.grch_hi <= p.grch_lo) return;
     size_t smem = (size_t)((p.t.huff_entries + 7) & ~7u) * 2;
-    unsigned blocks = (unsigned)((p.n_grch + 127) / 128);
+    unsigned blocks = (unsigned)((p.grch_hi - p.grch_lo + 127) / 128);
     l3_entropy_kernel<<<blocks, 128, smem, s>>>(p);
 }
 

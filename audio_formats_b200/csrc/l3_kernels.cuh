@@ -53,6 +53,7 @@ struct BatchParams {
     uint4* is;       // [n_grch][72] packed int16x8
     uint8_t* sf;     // [n_grch][96]
     float* pcm;
+    uint64_t grch_lo, grch_hi;  // granule-channel range the entropy kernel covers in this launch
     int zero_fill;   // entropy kernel writes all 72 chunks (tap mode)
     DeviceTables t;
 };
