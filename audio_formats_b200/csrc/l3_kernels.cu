@@ -377,6 +377,7 @@ template <> struct VT<1> {
     static __device__ __forceinline__ T sel(bool c0, bool, T a, T b) { return c0 ? a : b; }
     static __device__ __forceinline__ float ch(T a, int) { return a; }
     static __device__ __forceinline__ T pack(float a, float) { return a; }
+    static __device__ __forceinline__ T flip(T a, uint32_t signmask) { return __uint_as_float(__float_as_uint(a) ^ signmask); }
 };
 template <> struct VT<2> {
     typedef float2 T;
@@ -409,6 +410,9 @@ template <> struct VT<2> {
     static __device__ __forceinline__ T sel(bool c0, bool c1, T a, T b) { return make_float2(c0 ? a.x : b.x, c1 ? a.y : b.y); }
     static __device__ __forceinline__ float ch(T a, int c) { return c ? a.y : a.x; }
     static __device__ __forceinline__ T pack(float a, float b) { return make_float2(a, b); }
+    static __device__ __forceinline__ T flip(T a, uint32_t signmask) {
+        return make_float2(__uint_as_float(__float_as_uint(a.x) ^ signmask), __uint_as_float(__float_as_uint(a.y) ^ signmask));
+    }
 };
 
 // L3_ldexp_q2 (minimp3.d:646-657): y * 2^(-exp_q2/4) by repeated multiplication, same rounding steps.
@@ -896,10 +900,9 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             }
             __syncwarp();  // every lane has consumed its inputs; the buffer is reused in the padded (x19) layout
             if (mode >= 1) {
-                if (lane & 1) {
+                const uint32_t fm = (lane & 1) ? 0x80000000u : 0u;   // L3_change_sign: odd samples of odd bands
 #pragma unroll
-                    for (int i = 1; i < 18; i += 2) y[i] = V::neg(y[i]);
-                }
+                for (int i = 1; i < 18; i += 2) y[i] = V::flip(y[i], fm);
 #pragma unroll
                 for (int i = 0; i < 18; i++) xr[lane * 19 + i] = y[i];
             }

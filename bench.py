@@ -45,12 +45,17 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+WORKLOAD = "config2"   # set from --workload; config2 is the BASELINE.json metric configuration
+
+
 def gen_streams(seeds, seconds, threads):
     from audio_formats_b200 import synth
     synth.build()
+    maker = {"config2": synth.config2_params, "config3": synth.config3_params, "config4": synth.config4_params,
+             "config5": synth.config5_params}[WORKLOAD]
 
     def one(seed):
-        return synth.generate(synth.config2_params(seed, seconds))
+        return synth.generate(maker(seed, seconds))
 
     with ThreadPoolExecutor(threads) as ex:
         return list(ex.map(one, seeds))
@@ -154,6 +159,10 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, n_streams, note=""):
+    if WORKLOAD != "config2":
+        return {"workload": f"side measurement, generator profile {WORKLOAD}: {n_streams} streams x {args.seconds:g} s per GPU",
+                "streams_per_gpu": n_streams, "seconds_per_stream": args.seconds, "sharding": "by file, no collective",
+                "l2": "inputs larger than L2 (no flush needed)", **({"note": note} if note else {})}
     return {"workload": f"BASELINE.json configs[1]: {n_streams} synthetic {args.seconds:g} s 44.1 kHz stereo 128 kbps "
                         f"MPEG-1 Layer III long-block streams per GPU (seeds rank*streams+i)",
             "streams_per_gpu": n_streams, "seconds_per_stream": args.seconds, "sharding": "by file, no collective",
@@ -176,7 +185,11 @@ def main():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
+                    help="config2 is the metric configuration; the others are side measurements of the parity-test shapes")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.warmup < 3:
         args.warmup = 3
 
