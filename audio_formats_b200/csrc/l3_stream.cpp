@@ -38,8 +38,12 @@ struct l3b_stream {
     uint32_t cache_g0 = 0, cache_g1 = 0;
     bool error = false;
     std::string err;
+    l3b_resident_t* workspace = nullptr;  // device buffers recycled across decode-ahead windows
 
-    ~l3b_stream() { delete reader; }
+    ~l3b_stream() {
+        if (workspace) l3b_batch_free(ctx, workspace);
+        delete reader;
+    }
 };
 
 static void stream_restart(l3b_stream* s, uint64_t offset) {
@@ -101,7 +105,9 @@ static int decode_pending(l3b_stream* s) {
     b.n_streams = 1;
     b.pcm = s->cache.data() + old;
     b.pcm_floats = sd.pcm_count;
-    int rc = l3b_decode_batch(s->ctx, &b);
+    int rc = l3b_batch_upload_reuse(s->ctx, &b, &s->workspace);
+    if (!rc) rc = l3b_batch_run(s->ctx, s->workspace);
+    if (!rc) rc = l3b_batch_download(s->ctx, s->workspace, b.pcm, 0, b.pcm_floats);
     if (rc) {
         s->cache.resize(old);
         return rc;

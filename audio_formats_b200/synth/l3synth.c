@@ -202,7 +202,9 @@ static int next_block_type(const l3s_params_t* p, chan_state_t* cs, rng_t* r, in
     default: nt = rng_chance(r, 1, 8) ? 1 : 0; break;
     }
     cs->bt_state[ch] = nt;
-    if (nt == 2) *mixed = cs->mixed_run[ch];
+    /* 8 kHz mixed blocks are not generated: the reference's L3_reorder starts 72 coefficients in but walks a band
+     * table that assumes 48 (minimp3.d:1218, 1223 with the sfb row of 8 kHz) and runs past its 576-float buffer. */
+    if (nt == 2) *mixed = cs->mixed_run[ch] && p->hz != 8000;
     return nt;
 }
 

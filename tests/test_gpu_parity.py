@@ -145,3 +145,26 @@ def test_large_batch_sampled_against_oracle_and_checksums(ctx):
         (alone,) = ctx.decode_scans([scans[i]])
         assert zlib.crc32(alone.tobytes()) == batch_crc[i], i
     assert len(set(batch_crc)) == n                 # no two seeds collide: outputs are really per stream
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_generator_profiles(ctx, seed):
+    """Randomised sweep over the generator's knobs (format, bitrate, block switching, stereo mode, reservoir
+    pressure, scfsi, escapes, gain, level, CRC, tags): spectra and PCM stay bit-exact."""
+    from audio_formats_b200 import synth
+    rng = np.random.default_rng(1000 + seed)
+    hz = int(rng.choice([8000, 11025, 12000, 16000, 22050, 24000, 32000, 44100, 48000]))
+    nch = int(rng.integers(1, 3))
+    rates = [32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320] if hz >= 32000 else \
+            [8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160]
+    lo = 32 if hz >= 32000 else (16 if hz >= 16000 else 8)
+    rate = int(rng.choice([r for r in rates if r >= lo * nch and not (nch == 1 and hz >= 32000 and r > 192)]))
+    p = synth.SynthParams(seed=seed, hz=hz, nch=nch, bitrate_kbps=rate, nframes=int(rng.integers(12, 70)),
+                          block_mode=int(rng.integers(0, 2)), stereo_mode=int(rng.integers(0, 3)) if nch == 2 else 0,
+                          reservoir=int(rng.integers(0, 3)), scfsi=int(rng.integers(0, 2)), crc=int(rng.integers(0, 2)),
+                          escapes=int(rng.integers(0, 2)), gain_base=int(rng.integers(150, 200)),
+                          level=float(rng.choice([0.3, 1.0, 3.0, 8.0, 20.0])),
+                          small_scalefactors=int(rng.integers(0, 2)), table_cycle=int(rng.integers(0, 2)),
+                          table_cycle_pos=seed, no_padding=int(rng.integers(0, 2)),
+                          id3v2_bytes=int(rng.choice([0, 0, 10, 777])), id3v1=int(rng.integers(0, 2)))
+    check_stream(ctx, synth.generate(p, want_quantised=True), f"random[{seed}] {p}")
