@@ -724,6 +724,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             const uint8_t* rec1 = rec0 + (NCH - 1) * kSfRecBytes;
 
             // ---------------- band gains (minimp3.d:714-719) ----------------
+#ifndef L3B_EXP_SKIP_GAINS
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
                 const Desc& d = c ? d1 : d0;
@@ -739,11 +740,13 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                     W.scf[c][i] = v;
                 }
             }
+#endif
             if (istereo)
                 for (int i = lane; i < 40; i += 32) W.ist[i] = rec1[40 + i];
             __syncwarp();
 
             // ---------------- requantisation (minimp3.d:813-816, 846, 874-878) + MS stereo (:885-896) -------
+#ifndef L3B_EXP_SKIP_REQUANT
             {
                 const int nch0 = *reinterpret_cast<const uint16_t*>(rec0 + 80);
                 const int nch1 = *reinterpret_cast<const uint16_t*>(rec1 + 80);
@@ -773,6 +776,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                     }
                 }
             }
+#endif
             __syncwarp();
             // the staging buffers are free again: fetch the next granule while this one is transformed
             if (lane == 0 && it + 1 < n_iter) {
@@ -850,6 +854,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
         L3B_PHASE_SYNC();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
 
         // ---------------- reorder + antialias + IMDCT + frequency inversion (minimp3.d:1215-1229) ----------
+#ifndef L3B_EXP_SKIP_IMDCT
         if (act) {
             T x[18], y[18];
             const int bt0 = d0.block_type(), bt1 = d1.block_type();
@@ -896,7 +901,18 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 if (sh0) imdct_short_band<NCH>(x, ovl, y);
                 else imdct36_band<NCH>(x, ovl, bt0 == 3 ? 1 : 0, bt1 == 3 ? 1 : 0, y);
             } else {
-                imdct_split(x, ovl, y, sh0, sh1, bt0, bt1);
+                // Rare: the channels use different transforms in this band.  The out-of-line helper works on COPIES so
+                // that x / ovl / y themselves never have their address taken (they must stay in registers).
+                T xc[18], oc[9], yc[18];
+#pragma unroll
+                for (int i = 0; i < 18; i++) xc[i] = x[i];
+#pragma unroll
+                for (int i = 0; i < 9; i++) oc[i] = ovl[i];
+                imdct_split(xc, oc, yc, sh0, sh1, bt0, bt1);
+#pragma unroll
+                for (int i = 0; i < 18; i++) y[i] = yc[i];
+#pragma unroll
+                for (int i = 0; i < 9; i++) ovl[i] = oc[i];
             }
             __syncwarp();  // every lane has consumed its inputs; the buffer is reused in the padded (x19) layout
             if (mode >= 1) {
@@ -907,9 +923,11 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 for (int i = 0; i < 18; i++) xr[lane * 19 + i] = y[i];
             }
         }
+#endif
         L3B_PHASE_SYNC();
 
         // ---------------- DCT-32 matrixing across bands, one time slot per lane (minimp3.d:1232-1298) -------
+#ifndef L3B_EXP_SKIP_DCT
         if (act && mode >= 1 && lane < 18) {
             T t[4][8];
 #pragma unroll
@@ -967,9 +985,11 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             out[30] = t[1][7];
             out[31] = t[3][7];
         }
+#endif
         L3B_PHASE_SYNC();
 
         // ---------------- 512-tap window (minimp3.d:1305-1406) ----------------
+#ifndef L3B_EXP_SKIP_WINDOW
         if (act && mode == 2) {
             const uint64_t f0 = (uint64_t)g * 576u;   // first frame of this granule in the decoded signal
             const bool inside = f0 >= skipf && f0 + 576u <= skipf + countf;
@@ -1047,6 +1067,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 if (inside || (f0 + fb >= skipf && f0 + fb - skipf < countf)) out[fb] = V::muls(a, scale);
             }
         }
+#endif
         // slide the history: the last 15 slots become rows 0..14 (qmf_state, minimp3.d:1423-1433)
         if (act && mode >= 1) {
             __syncwarp();
