@@ -753,9 +753,15 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 const uint32_t* isw0 = reinterpret_cast<const uint32_t*>(W.st_is);
                 const uint32_t* isw1 = isw0 + (NCH - 1) * (kIsChunks * 4);
                 const bool ms_now = NCH == 2 && ms_frame && !istereo;
+                const int nz_hi = max(nch0, NCH == 2 ? nch1 : 0);   // chunks (8 coefficients) holding anything non-zero
 #pragma unroll 3
                 for (int m = 0; m < 9; m++) {
                     const int pi = lane + 32 * m;
+                    if (8 * m >= nz_hi) {   // warp-uniform: both channels are zero from here on (+0.0, like the memset grbuf)
+                        if (NCH == 2) *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        else *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(0.0f, 0.0f);
+                        continue;
+                    }
                     const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;   // chunks past nz_chunks were never written
                     const float sa = W.scf[0][W.sfbpair[kind0][pi]];
                     float a0 = requant(s_pow43, (int)(int16_t)(va & 0xFFFFu), sa);
