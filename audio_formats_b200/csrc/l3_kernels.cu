@@ -611,7 +611,7 @@ struct __align__(16) WarpSmem {
 };
 
 // The (rare) band where the two channels of a granule use different transforms: one channel at a time.
-__device__ __noinline__ void imdct_split(float2* x, float2* ovl, float2* y, bool sh0, bool sh1, int bt0, int bt1) {
+__device__ __noinline__ void imdct_split(float2* x, float2* ovl, float2* y, bool sh0, bool sh1, int ws0, int ws1) {
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         float xs[18], os[9], ys[18];
@@ -620,7 +620,7 @@ __device__ __noinline__ void imdct_split(float2* x, float2* ovl, float2* y, bool
 #pragma unroll
         for (int i = 0; i < 9; i++) os[i] = c ? ovl[i].y : ovl[i].x;
         if (c ? sh1 : sh0) imdct_short_band<1>(xs, os, ys);
-        else imdct36_band<1>(xs, os, (c ? bt1 : bt0) == 3 ? 1 : 0, 0, ys);
+        else imdct36_band<1>(xs, os, c ? ws1 : ws0, 0, ys);
 #pragma unroll
         for (int i = 0; i < 18; i++) { if (c) y[i].y = ys[i]; else y[i].x = ys[i]; }
 #pragma unroll
@@ -903,9 +903,14 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 }
             }
             const bool sh0 = bt0 == 2 && lane >= nlb0, sh1 = bt1 == 2 && lane >= nlb1;
+            // window row: the stop window, except in the long bands of a granule whose mixed_block_flag is set --
+            // the reference honours the flag on every block type (minimp3.d:1212, 1158-1167), so a STOP block that
+            // closes a mixed run keeps the normal window in its lowest bands
+            const int ws0 = (bt0 == 3 && lane >= (d0.mixed() ? n_long_bands_mixed : 0)) ? 1 : 0;
+            const int ws1 = (bt1 == 3 && lane >= (d1.mixed() ? n_long_bands_mixed : 0)) ? 1 : 0;
             if (NCH == 1 || sh0 == sh1) {
                 if (sh0) imdct_short_band<NCH>(x, ovl, y);
-                else imdct36_band<NCH>(x, ovl, bt0 == 3 ? 1 : 0, bt1 == 3 ? 1 : 0, y);
+                else imdct36_band<NCH>(x, ovl, ws0, ws1, y);
             } else {
                 // Rare: the channels use different transforms in this band.  The out-of-line helper works on COPIES so
                 // that x / ovl / y themselves never have their address taken (they must stay in registers).
@@ -914,7 +919,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 for (int i = 0; i < 18; i++) xc[i] = x[i];
 #pragma unroll
                 for (int i = 0; i < 9; i++) oc[i] = ovl[i];
-                imdct_split(xc, oc, yc, sh0, sh1, bt0, bt1);
+                imdct_split(xc, oc, yc, sh0, sh1, ws0, ws1);
 #pragma unroll
                 for (int i = 0; i < 18; i++) y[i] = yc[i];
 #pragma unroll

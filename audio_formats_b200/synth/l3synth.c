@@ -190,21 +190,26 @@ static int next_block_type(const l3s_params_t* p, chan_state_t* cs, rng_t* r, in
     if (!p->block_mode) return 0;
     int st = cs->bt_state[ch], nt;
     switch (st) {
-    case 0: nt = rng_chance(r, 1, 6) ? 1 : 0; break;
+    case 0:
+    default:
+        nt = rng_chance(r, 1, st == 0 ? 6 : 8) ? 1 : 0;
+        /* whether the coming short run is mixed is decided with its START block: an encoder that keeps the two
+         * lowest subbands on long transforms signals mixed_block_flag on the start, short and stop blocks alike
+         * (ISO 11172-3 2.4.2.7), and the reference honours the flag on all of them (minimp3.d:1212, 1158-1167) */
+        if (nt == 1) cs->mixed_run[ch] = p->block_mode == 1 ? rng_chance(r, 1, 3) : 0;
+        break;
     case 1:
         nt = 2;
         cs->short_left[ch] = 1 + (int)rng_below(r, 3);
-        cs->mixed_run[ch] = rng_chance(r, 1, 3);
         break;
     case 2:
         if (--cs->short_left[ch] > 0) nt = 2; else nt = 3;
         break;
-    default: nt = rng_chance(r, 1, 8) ? 1 : 0; break;
     }
     cs->bt_state[ch] = nt;
     /* 8 kHz mixed blocks are not generated: the reference's L3_reorder starts 72 coefficients in but walks a band
      * table that assumes 48 (minimp3.d:1218, 1223 with the sfb row of 8 kHz) and runs past its 576-float buffer. */
-    if (nt == 2) *mixed = cs->mixed_run[ch] && p->hz != 8000;
+    if (nt == 2 || (nt != 0 && !p->mixed_only_short)) *mixed = cs->mixed_run[ch] && p->hz != 8000;
     return nt;
 }
 

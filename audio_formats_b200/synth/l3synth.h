@@ -13,7 +13,7 @@ typedef struct {
     int nch;           /* 1 or 2 */
     int bitrate_kbps;  /* a legal Layer III rate for that version */
     int nframes;
-    int block_mode;    /* 0: long blocks only; 1: long->start->short(xN, 1/3 mixed)->stop sequences */
+    int block_mode;    /* 0: long blocks only; 1: long->start->short(xN, 1/3 of the runs mixed)->stop sequences; 2: same, never mixed */
     int stereo_mode;   /* 0: plain stereo; 1: joint with MS on ~half the frames; 2: joint with MS and intensity */
     int reservoir;     /* 0: main_data_begin always 0; 1: moderate; 2: heavy (sparse/dense alternation) */
     int scfsi;         /* 1: exercise scfsi on granule 1 */
@@ -28,6 +28,7 @@ typedef struct {
     int id3v2_bytes;   /* >= 10: prepend an ID3v2 tag of that total size */
     int id3v1;         /* 1: append a 128-byte ID3v1 tag */
     int emphasis_bits; /* low 4 bits of header byte 3 (copyright/original/emphasis) */
+    int mixed_only_short; /* 1: mixed_block_flag only on the short blocks of a mixed run, not on its start/stop blocks */
 } l3s_params_t;
 
 typedef struct {

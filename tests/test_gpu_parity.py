@@ -58,6 +58,20 @@ def test_config4_heterogeneous(ctx, seed):
     check_stream(ctx, synth.generate(p, want_quantised=True), f"config4[{seed}] {p.hz} Hz {p.nch} ch {p.bitrate_kbps} kbps")
 
 
+@pytest.mark.parametrize("only_short", [0, 1])
+@pytest.mark.parametrize("hz,rate", [(44100, 128), (22050, 64), (48000, 192)])
+def test_mixed_block_flag_on_start_and_stop_blocks(ctx, hz, rate, only_short):
+    """The reference derives n_long_bands from mixed_block_flag on EVERY block type (minimp3.d:1212): a STOP block
+    carrying the flag keeps the normal window in its lowest bands.  only_short=1 is the inconsistent signalling
+    (flag on the short blocks only) where the reference departs from ISO decoders; we follow the reference."""
+    from audio_formats_b200 import synth
+    for nch in (1, 2):
+        p = synth.SynthParams.for_seconds(4.0, hz=hz, seed=900 + hz // 100 + nch, nch=nch, bitrate_kbps=rate if nch == 2 else rate // 2,
+                                          block_mode=1, stereo_mode=1 if nch == 2 else 0, small_scalefactors=0,
+                                          mixed_only_short=only_short)
+        check_stream(ctx, synth.generate(p, want_quantised=True), f"mixed flag {hz} {nch}ch only_short={only_short}")
+
+
 def test_config5_320kbps(ctx):
     from audio_formats_b200 import synth
     check_stream(ctx, synth.generate(synth.config5_params(5, 6.0), want_quantised=True), "config5")
@@ -166,5 +180,6 @@ def test_random_generator_profiles(ctx, seed):
                           level=float(rng.choice([0.3, 1.0, 3.0, 8.0, 20.0])),
                           small_scalefactors=int(rng.integers(0, 2)), table_cycle=int(rng.integers(0, 2)),
                           table_cycle_pos=seed, no_padding=int(rng.integers(0, 2)),
-                          id3v2_bytes=int(rng.choice([0, 0, 10, 777])), id3v1=int(rng.integers(0, 2)))
+                          id3v2_bytes=int(rng.choice([0, 0, 10, 777])), id3v1=int(rng.integers(0, 2)),
+                          mixed_only_short=int(seed % 3 == 0))
     check_stream(ctx, synth.generate(p, want_quantised=True), f"random[{seed}] {p}")
