@@ -42,6 +42,8 @@ struct l3b_resident {
     uint8_t* d_sf = nullptr;
     float* d_pcm = nullptr;
     Tile* d_tiles[2] = {nullptr, nullptr};  // [0] stereo, [1] mono
+    HuffJob* d_jobs = nullptr;              // one per granule-channel, written by the scalefactor kernel
+    uint32_t* d_counters = nullptr;         // 2 per sub-batch: item counters of the two Huffman kernels
     uint32_t n_tiles[2] = {0, 0};
     uint64_t n_grch = 0, pcm_floats = 0;
     uint32_t n_streams = 0;
@@ -102,6 +104,7 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** out) {
 
     // lookup tables: one device allocation, sub-allocated at 256-byte granularity
     HuffLut hl = build_huff_lut();
+    HuffLut32 hl32 = build_huff_lut32();
     SfbMaps* sm = new SfbMaps();
     build_sfb_maps(sm);
     std::vector<uint8_t> img;
@@ -113,6 +116,9 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** out) {
     };
     size_t o_huff = put(hl.entries.data(), hl.entries.size() * 2);
     size_t o_c1 = put(hl.count1, sizeof hl.count1);
+    size_t o_huff32 = put(hl32.entries.data(), hl32.entries.size() * 4);
+    size_t o_c1code = put(hl32.c1code, sizeof hl32.c1code);
+    size_t o_c1val = put(hl32.c1val, sizeof hl32.c1val);
     size_t o_pair = put(sm->sfb_of_pair, sizeof sm->sfb_of_pair);
     size_t o_w = put(sm->width, sizeof sm->width);
     size_t o_s = put(sm->start, sizeof sm->start);
@@ -127,6 +133,11 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** out) {
     c->t.huff_entries = (uint32_t)hl.entries.size();
     for (int i = 0; i < 18; i++) { c->t.huff_base[i] = hl.base[i]; c->t.huff_root[i] = hl.root_bits[i]; }
     c->t.count1 = base + o_c1;
+    c->t.huff32 = reinterpret_cast<const uint32_t*>(base + o_huff32);
+    c->t.huff32_entries = (uint32_t)hl32.entries.size();
+    for (int i = 0; i < 16; i++) { c->t.huff32_base[i] = hl32.base[i]; c->t.huff32_root[i] = hl32.root_bits[i]; }
+    c->t.c1code = reinterpret_cast<const uint16_t*>(base + o_c1code);
+    c->t.c1val = reinterpret_cast<const uint2*>(base + o_c1val);
     c->t.sfb_of_pair = base + o_pair;
     c->t.sfb_width = base + o_w;
     c->t.sfb_start = reinterpret_cast<const uint16_t*>(base + o_s);
@@ -134,6 +145,7 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** out) {
     c->t.pow43 = reinterpret_cast<const float*>(base + o_pow);
     c->t.win = reinterpret_cast<const float*>(base + o_win);
     upload_constants();
+    upload_entropy_constants();
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail("constant upload", e);
     *out = c;
     return 0;
@@ -173,6 +185,8 @@ void l3b_batch_free(l3b_ctx_t* c, l3b_resident_t* r) {
     cudaFree(r->d_pcm);
     cudaFree(r->d_tiles[0]);
     cudaFree(r->d_tiles[1]);
+    cudaFree(r->d_jobs);
+    cudaFree(r->d_counters);
     delete r;
 }
 
@@ -255,13 +269,15 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
         CU_TRY_R(cudaMalloc(&r->d_blob, r->cap_blob));
     }
     if (b->n_grch > r->cap_grch || !r->d_grch) {
-        cudaFree(r->d_grch); cudaFree(r->d_is); cudaFree(r->d_sf);
-        r->d_grch = nullptr; r->d_is = nullptr; r->d_sf = nullptr;
+        cudaFree(r->d_grch); cudaFree(r->d_is); cudaFree(r->d_sf); cudaFree(r->d_jobs);
+        r->d_grch = nullptr; r->d_is = nullptr; r->d_sf = nullptr; r->d_jobs = nullptr;
         r->cap_grch = std::max<uint64_t>(1, grow(b->n_grch));
         CU_TRY_R(cudaMalloc(&r->d_grch, r->cap_grch * sizeof(l3b_grch_desc_t)));
         CU_TRY_R(cudaMalloc(&r->d_is, r->cap_grch * kIsChunks * sizeof(uint4)));
         CU_TRY_R(cudaMalloc(&r->d_sf, r->cap_grch * kSfRecBytes));
+        CU_TRY_R(cudaMalloc(&r->d_jobs, r->cap_grch * sizeof(HuffJob)));
     }
+    if (!r->d_counters) CU_TRY_R(cudaMalloc(&r->d_counters, 2 * l3b_ctx::kMaxSubs * sizeof(uint32_t)));
     if (b->pcm_floats > r->cap_pcm || !r->d_pcm) {
         cudaFree(r->d_pcm); r->d_pcm = nullptr;
         r->cap_pcm = std::max<uint64_t>(4, grow(b->pcm_floats));
@@ -302,6 +318,8 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     p.is = r->d_is;
     p.sf = r->d_sf;
     p.pcm = r->d_pcm;
+    p.jobs = r->d_jobs;
+    p.counters = r->d_counters;
     p.zero_fill = b->taps ? 1 : 0;
     p.t = c->t;
     *inout = r;
@@ -340,13 +358,19 @@ int l3b_batch_run(l3b_ctx_t* c, l3b_resident_t* r) {
     CU_TRY(c, cudaEventRecord(ev[0], A));
     CU_TRY(c, cudaStreamWaitEvent(B, ev[0], 0));   // uploads on A are complete before anything on B starts
     int launches = 0;
+    static const bool entropy_v3 = getenv("L3B_ENTROPY") && !strcmp(getenv("L3B_ENTROPY"), "v3");   // A/B switch: the lockstep kernel
+    if (!entropy_v3) CU_TRY(c, cudaMemsetAsync(r->d_counters, 0, 2 * l3b_ctx::kMaxSubs * sizeof(uint32_t), A));
     for (int i = 0; i < ns; i++) {
         const l3b_resident::Sub& sb = r->subs[i];
         BatchParams p = r->params;
         p.grch_lo = sb.grch_lo;
         p.grch_hi = sb.grch_hi;
-        launch_entropy(p, A);
-        launches += sb.grch_hi > sb.grch_lo;
+        if (entropy_v3) {
+            launch_entropy(p, A);
+            launches += sb.grch_hi > sb.grch_lo;
+        } else {
+            launches += launch_entropy_v4(p, i, A);
+        }
         cudaEvent_t* se = ev + 3 + 3 * i;
         CU_TRY(c, cudaEventRecord(se[0], A));
         CU_TRY(c, cudaStreamWaitEvent(B, se[0], 0));   // granule kernels of sub-batch i wait for its spectra only

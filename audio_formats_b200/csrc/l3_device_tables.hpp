@@ -96,6 +96,89 @@ inline HuffLut build_huff_lut() {
     return L;
 }
 
+// ---- Huffman decode LUT, 32-bit entries (the lane-decoupled entropy kernels) ---------------------------
+// Per book a root table of 2^root_bits entries followed by its sub-tables, fields placed so that the common path
+// needs no masking beyond what the shifter does for free:
+//   leaf : [a0:4 @0][tot:4 @4][len:4 @8][n1 @15][a1:4 @16][n0 @24][esc @30]
+//          len = code bits consumed at THIS level (0..8); n0/n1 = a0/a1 non-zero; tot = len + n0 + n1 (code + sign bits);
+//          esc = the book has linbits and a0 or a1 is 15 (minimp3.d:805-813): taken out of line
+//   link : bit31 = 1 : [offset:16 @0][32-width:5 @16][adv:5 @22]   offset relative to the book's base, width of the
+//          sub-table, adv = bits to consume before descending (the width of the table holding the link)
+// Book L3_NBOOKS is the all-zero book (table_select 0/4/14).  The count1 books are separate tables:
+//   c1code[t][6-bit peek] = len | flags<<4 | (len + popcount(flags))<<8       (minimp3.d:857-866)
+//   c1val[flags<<4 | s]   = the quad's two packed int16x2 words when the next four bits are s: sign bits are consumed
+//                           by the non-zero values in order v0..v3 (minimp3.d:869-878)
+struct HuffLut32 {
+    std::vector<uint32_t> entries;
+    uint32_t base[L3_NBOOKS + 1];
+    uint8_t root_bits[L3_NBOOKS + 1];
+    uint16_t c1code[2][64];
+    uint32_t c1val[256][2];
+};
+
+namespace detail {
+inline void build_level32(int book, bool has_linbits, std::vector<uint32_t>& e, size_t book_base, uint32_t prefix, int plen, int width) {
+    size_t at = e.size();
+    e.resize(at + ((size_t)1 << width), 0);
+    for (uint32_t v = 0; v < (1u << width); v++) {
+        uint32_t bits = (prefix << width) | v;
+        bool done = false;
+        for (int l = plen + 1; l <= plen + width && !done; l++) {
+            int s = find_code(book, l, bits >> (plen + width - l));
+            if (s >= 0) {
+                const uint32_t a0 = (uint32_t)(s >> 4), a1 = (uint32_t)(s & 15), len = (uint32_t)(l - plen);
+                const uint32_t n0 = a0 != 0, n1 = a1 != 0;
+                const uint32_t esc = has_linbits && (a0 == 15 || a1 == 15);
+                e[at + v] = a0 | ((len + n0 + n1) << 4) | (len << 8) | (n1 << 15) | (a1 << 16) | (n0 << 24) | (esc << 30);
+                done = true;
+            }
+        }
+        if (!done) {
+            int rest = longest_under(book, bits, plen + width) - (plen + width);
+            int w = rest > 8 ? 8 : rest;
+            size_t child = e.size() - book_base;
+            e[at + v] = 0x80000000u | (uint32_t)child | ((uint32_t)(32 - w) << 16) | ((uint32_t)width << 22);
+            build_level32(book, has_linbits, e, book_base, bits, plen + width, w);
+        }
+    }
+}
+}  // namespace detail
+
+inline HuffLut32 build_huff_lut32() {
+    HuffLut32 L;
+    for (int b = 0; b < L3_NBOOKS; b++) {
+        int rb = L3_BOOK_MAXLEN[b] < 8 ? L3_BOOK_MAXLEN[b] : 8;
+        bool lin = false;
+        for (int sel = 0; sel < 32; sel++) lin |= (L3_SEL2BOOK[sel] == b && L3_LINBITS[sel] != 0);
+        L.base[b] = (uint32_t)L.entries.size();
+        L.root_bits[b] = (uint8_t)rb;
+        detail::build_level32(b, lin, L.entries, L.entries.size(), 0, 0, rb);
+    }
+    L.base[L3_NBOOKS] = (uint32_t)L.entries.size();
+    L.root_bits[L3_NBOOKS] = 1;
+    L.entries.push_back(0);
+    L.entries.push_back(0);
+    memset(L.c1code, 0, sizeof L.c1code);
+    for (int t = 0; t < 2; t++)
+        for (int v = 0; v < 64; v++)
+            for (int f = 0; f < 16; f++) {
+                int ln = L3_C1LEN[t * 16 + f];
+                if ((v >> (6 - ln)) == L3_C1CODE[t * 16 + f])
+                    L.c1code[t][v] = (uint16_t)(ln | (f << 4) | ((ln + __builtin_popcount((unsigned)f)) << 8));
+            }
+    for (int f = 0; f < 16; f++)
+        for (int s = 0; s < 16; s++) {
+            int val[4], k = 0;
+            for (int i = 0; i < 4; i++) {
+                val[i] = 0;
+                if (f & (8 >> i)) { val[i] = (s & (8 >> k)) ? -1 : 1; k++; }
+            }
+            L.c1val[f * 16 + s][0] = ((uint32_t)val[0] & 0xFFFFu) | ((uint32_t)val[1] << 16);
+            L.c1val[f * 16 + s][1] = ((uint32_t)val[2] & 0xFFFFu) | ((uint32_t)val[3] << 16);
+        }
+    return L;
+}
+
 // ---- scalefactor-band maps -----------------------------------------------------------------------
 // kind: 0 long, 1 short, 2 mixed.   sfb_of_pair[row][kind][p] = sfb index of coefficients 2p, 2p+1.
 struct SfbMaps {

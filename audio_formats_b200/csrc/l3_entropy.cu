@@ -1,0 +1,602 @@
+// l3_entropy.cu -- lane-decoupled entropy decode (integer only): scalefactors, big_values, count1.
+//
+// The Huffman data of a granule-channel is a serial bit stream, so the unit of parallelism is the granule-channel and
+// its cost (pairs + quads actually coded) varies by 10x from one to the next.  A warp that owns 32 fixed
+// granule-channels runs as long as its slowest lane: on the 128 kbps bench streams that wastes half of all lane
+// slots.  Here the lanes of a warp are decoupled instead:
+//
+//   l3_scf_kernel       one thread per granule-channel: scalefactors (minimp3.d:613-644, 659-712) -> scalefactor
+//                       record; and a 32-byte HuffJob (bit window, region books, limits) for the two kernels below
+//   l3_huff_big_kernel  persistent warps; every LANE pulls granule-channels from a global counter and decodes their
+//                       big_values pairs (minimp3.d:789-853), four pairs (one 16-byte chunk) per trip; a lane that
+//                       runs out of pairs parks until enough lanes are free, then they refill together
+//   l3_huff_c1_kernel   same scheme for the count1 quads (minimp3.d:855-882), continuing at the bit position the
+//                       big_values kernel left in the job
+//
+// Keeping the two Huffman phases in separate kernels keeps every warp on ONE straight-line code path: a warp whose
+// lanes sit in different phases would have to run both.  Output format is unchanged: int16 spectra as 72 16-byte
+// chunks per granule-channel, `nz_chunks` in the scalefactor record.
+#include "l3_kernels.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "l3_desc.cuh"
+#include "l3_tables_gen.h"
+
+namespace l3b {
+
+__constant__ uint8_t e_partitions[84];
+__constant__ uint8_t e_scfc_decode[16];
+__constant__ uint8_t e_lsf_mod[24];
+__constant__ uint8_t e_preamp[10];
+__constant__ uint8_t e_linbits[32];
+__constant__ int8_t e_sel2book[32];
+
+void upload_entropy_constants() {
+    cudaMemcpyToSymbol(e_partitions, L3_SCF_PARTITIONS, sizeof e_partitions);
+    cudaMemcpyToSymbol(e_scfc_decode, L3_SCFC_DECODE, sizeof e_scfc_decode);
+    cudaMemcpyToSymbol(e_lsf_mod, L3_LSF_MOD, sizeof e_lsf_mod);
+    cudaMemcpyToSymbol(e_preamp, L3_PREAMP, sizeof e_preamp);
+    cudaMemcpyToSymbol(e_linbits, L3_LINBITS, sizeof e_linbits);
+    cudaMemcpyToSymbol(e_sel2book, L3_SEL2BOOK, sizeof e_sel2book);
+}
+
+namespace {
+
+// MSB-first bit reader over the 32-bit words of a stream's main data (scalefactor fields only).
+struct ScfReader {
+    const uint32_t* words;
+    uint32_t nwords, pos;
+    // nwords counts the 16 zero pad bytes that follow every stream, so clamping the index makes reads past the end
+    // return zero bits without a branch
+    __device__ __forceinline__ uint32_t ldw(uint32_t i) const { return __byte_perm(__ldg(words + min(i, nwords - 1)), 0, 0x0123); }
+    __device__ __forceinline__ uint32_t peek_at(uint32_t at, int n) const {   // 1 <= n <= 16
+        const uint32_t wi = at >> 5;
+        return __funnelshift_l(ldw(wi + 1), ldw(wi), at) >> (32 - n);
+    }
+    __device__ __forceinline__ uint32_t get(int n) { const uint32_t v = peek_at(pos, n); pos += (uint32_t)n; return v; }
+};
+
+__device__ __forceinline__ uint32_t find_stream(const l3b_stream_desc_t* streams, uint32_t n, uint64_t gi) {
+    uint32_t lo = 0, hi = n - 1;
+    while (lo < hi) {  // last stream with first_grch <= gi
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (streams[mid].first_grch <= gi) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// Scalefactors + job setup: one thread per granule-channel
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
+    const uint64_t gi = p.grch_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= p.grch_hi) return;
+    const uint32_t si = find_stream(p.streams, p.n_streams, gi);
+    const l3b_stream_desc_t* S = p.streams + si;
+    const int nch = S->nch;
+    const int ch = (int)((gi - S->first_grch) % (uint64_t)nch);
+    const bool mpeg1 = S->mpeg1 != 0;
+    ScfReader br;
+    br.words = reinterpret_cast<const uint32_t*>(p.blob + S->maindata_off);
+    br.nwords = (S->maindata_bytes >> 2) + 4;  // the batch blob keeps >= 16 zero bytes after each stream
+    const Desc d = load_desc(p.grch + gi);
+    br.pos = d.bit_start;
+
+    // ---------------- scalefactors (minimp3.d:613-644, 659-712) ----------------
+    uint32_t recw[kSfRecBytes / 4];
+#pragma unroll
+    for (int i = 0; i < kSfRecBytes / 4; i++) recw[i] = 0;
+    uint8_t* const rec = reinterpret_cast<uint8_t*>(recw);   // thread-local staging of the record (local memory, 96 B)
+    const int kind = d.kind();
+    const int n_long = kind == 0 ? 22 : (kind == 1 ? 0 : (mpeg1 ? 8 : 6));
+    const int n_short = kind == 0 ? 0 : (kind == 1 ? 39 : 30);
+    const uint8_t* part = e_partitions + 28 * (kind == 0 ? 0 : (kind == 2 ? 1 : 2));
+    const int scf_shift = d.scalefac_scale() + 1;
+    uint32_t slen = 0;  // four byte-sized lengths
+    int scfsi = d.scfsi();
+    const int istereo = d.hdr_bits() & 1;
+    if (mpeg1) {
+        const int pp = e_scfc_decode[d.scalefac_compress() & 15];
+        const uint32_t a = (uint32_t)(pp >> 2), b = (uint32_t)(pp & 3);
+        slen = a | (a << 8) | (b << 16) | (b << 24);
+    } else {
+        const int ist = (istereo && ch) ? 1 : 0;
+        int sfc = d.scalefac_compress() >> ist;
+        int k = ist * 12;
+        for (;; k += 4) {
+            int modprod = 1;
+            slen = 0;
+#pragma unroll
+            for (int i = 3; i >= 0; i--) {
+                const int m = e_lsf_mod[k + i];
+                slen |= (uint32_t)(sfc / modprod % m) << (8 * i);
+                modprod *= m;
+            }
+            sfc -= modprod;
+            if (sfc < 0) break;
+        }
+        part += k + 4;  // the reference's for-loop increments k once more before its exit test (minimp3.d:683-691)
+        scfsi = -16;
+    }
+    // granule-0 scalefactors for scfsi copies (MPEG-1 granule 1 only; both granules are long blocks then)
+    uint32_t g0_slen = 0, g0_bits = 0;
+    if (scfsi > 0 && d.second_granule() && gi >= S->first_grch + (uint64_t)nch) {
+        const Desc d0 = load_desc(p.grch + gi - nch);
+        const int pp = e_scfc_decode[d0.scalefac_compress() & 15];
+        const uint32_t a = (uint32_t)(pp >> 2), b = (uint32_t)(pp & 3);
+        g0_slen = a | (a << 8) | (b << 16) | (b << 24);
+        g0_bits = d0.bit_start;
+    } else if (scfsi > 0) {
+        scfsi = 0;  // no granule 0 to copy from
+    }
+    {
+        const int sbg_sh = 3 - scf_shift;
+        int n = 0;
+        uint32_t g0_off = g0_bits;
+        for (int i = 0; i < 4; i++) {
+            const int cnt = part[i];
+            if (!cnt) break;
+            const int bits = (slen >> (8 * i)) & 0xFF;
+            const int bits0 = (g0_slen >> (8 * i)) & 0xFF;
+            const bool copy = (scfsi & 8) != 0;
+            for (int k = 0; k < cnt; k++, n++) {
+                int s, ip;
+                if (copy) {
+                    s = bits0 ? (int)br.peek_at(g0_off + (uint32_t)(k * bits0), bits0) : 0;
+                    ip = s;
+                } else if (!bits) {
+                    s = 0; ip = 0;
+                } else {
+                    s = (int)br.get(bits);
+                    ip = (scfsi < 0 && s == (1 << bits) - 1) ? 255 : s;
+                }
+                int adj = 0;
+                if (n_short) { if (n >= n_long) adj = d.subblock_gain((n - n_long) % 3) << sbg_sh; }
+                else if (d.preflag() && n >= 11 && n < 21) adj = e_preamp[n - 11];
+                rec[n] = (uint8_t)(s + adj);
+                rec[40 + n] = (uint8_t)ip;
+            }
+            g0_off += (uint32_t)(cnt * bits0);
+            scfsi *= 2;
+        }
+        for (int j = 0; j < 3 && n < 40; j++, n++) {  // scf[0] = scf[1] = scf[2] = 0 after the last partition
+            int adj = 0;
+            if (n_short) { if (n >= n_long && n < n_long + n_short) adj = d.subblock_gain((n - n_long) % 3) << sbg_sh; }
+            rec[n] = (uint8_t)adj;
+        }
+    }
+    {
+        uint4* dst = reinterpret_cast<uint4*>(p.sf + gi * kSfRecBytes);
+#pragma unroll
+        for (int i = 0; i < kSfRecBytes / 16; i++) dst[i] = make_uint4(recw[4 * i], recw[4 * i + 1], recw[4 * i + 2], recw[4 * i + 3]);
+    }
+
+    // ---------------- Huffman job ----------------
+    HuffJob j;
+    j.word_base = (uint32_t)(S->maindata_off >> 2);
+    j.nwords = br.nwords;
+    j.pos = br.pos;
+    j.limit = d.bit_start + (uint32_t)d.part23();
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const int sel = d.table_select(r);
+        const int book = e_sel2book[sel] < 0 ? L3_NBOOKS : e_sel2book[sel];
+        j.par[r] = p.t.huff32_base[book] | ((32u - p.t.huff32_root[book]) << 16) | ((uint32_t)e_linbits[sel] << 24);
+    }
+    j.misc = (uint32_t)d.big_values() | ((uint32_t)(d.region1_start() >> 1) << 10) | ((uint32_t)(d.region2_start() >> 1) << 20) |
+             ((uint32_t)d.count1_table() << 30);
+    const uint32_t wi = br.pos >> 5;
+    uint4* jd = reinterpret_cast<uint4*>(p.jobs + gi);
+    jd[0] = make_uint4(j.word_base, j.nwords, j.pos, j.limit);
+    jd[1] = make_uint4(j.par[0], j.par[1], j.par[2], j.misc);
+    {   // the first four words of the bit window (the last two in memory byte order): no dependent load at refill
+        const uint32_t* w = br.words;
+        const uint32_t last = br.nwords - 1;
+        jd[2] = make_uint4(br.ldw(wi), br.ldw(wi + 1), __ldg(w + min(wi + 2, last)), __ldg(w + min(wi + 3, last)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shared pieces of the two Huffman kernels
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr uint32_t kRingWords = 8;    // per-lane ring of prefetched bit-stream words (shared memory)
+constexpr uint32_t kAhead = 6;        // words requested beyond the one that enters the window next
+
+// shared-window address of p, made opaque so that the compiler keeps it in a register instead of re-deriving it
+// (S2R SR_CgaCtaId + LEA) at every use
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Window over the bit stream.  w0:w1 are the big-endian words holding bit `pos` and the 32 bits after it.  The words
+// behind them come from a per-lane ring in shared memory that is topped up with cp.async ONLY at trip boundaries:
+// a load issued inside a decode step would be waited for by the next step of every lane of the warp (scoreboards
+// are per warp, not per lane), which exposes the full memory latency once per step.  Requests made at one boundary
+// are waited for at the next one, a whole trip later.
+struct BitWindow {
+    const uint32_t* words;
+    uint32_t nwords, pos, w0, w1;
+    uint32_t wn;       // index of the word that enters w1 at the next crossing
+    uint32_t ready;    // words below this index have landed in the ring
+    uint32_t filled;   // words below this index have been requested
+    uint32_t ring;     // shared address of this lane's slot 0; word i lives at ring + (i % kRingWords) * 128
+
+    __device__ __forceinline__ uint32_t slot(uint32_t i) const { return ring + ((i & (kRingWords - 1)) << 7); }
+    __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_l(w1, w0, pos); }
+    __device__ __forceinline__ uint32_t raw_word(uint32_t i) const {   // memory byte order
+        if (i < ready) return lds32(slot(i));
+        return __ldg(words + min(i, nwords - 1));   // starved (escape-heavy data): direct load; nwords counts the zero pad
+    }
+    __device__ __forceinline__ void advance(uint32_t n) {   // n < 32
+        const uint32_t np = pos + n;
+        if ((np ^ pos) & ~31u) {
+            w0 = w1;
+            w1 = __byte_perm(raw_word(wn), 0, 0x0123);
+            wn++;
+        }
+        pos = np;
+    }
+    // job hand-over: bit position + four words starting at the one holding `pos`
+    __device__ __forceinline__ void open(const uint32_t* w, uint32_t nw, uint32_t bitpos, uint4 first) {
+        words = w; nwords = nw; pos = bitpos;
+        w0 = first.x; w1 = first.y;
+        wn = (bitpos >> 5) + 2;
+        sts32(slot(wn), first.z);
+        sts32(slot(wn + 1), first.w);
+        ready = filled = wn + 2;
+    }
+    __device__ __forceinline__ uint4 close() const { return make_uint4(w0, w1, raw_word(wn), raw_word(wn + 1)); }
+    // trip boundary: everything requested a trip ago has landed; request what the coming trips may need
+    __device__ __forceinline__ void top_up(bool live) {
+        cp_async_wait_all();
+        ready = filled;
+        if (live) {
+            const uint32_t want = wn + kAhead;
+            while (filled < want) {
+                cp_async4(slot(filled), words + min(filled, nwords - 1));
+                filled++;
+            }
+        }
+    }
+};
+
+// Work distribution.  A warp takes blocks of 32 consecutive jobs from a global counter (one atomic per block) and
+// keeps them in shared memory; its lanes draw from that pool one by one as they run out of work.  The following
+// block is already on its way into registers (three coalesced 16-byte loads per lane) while the current one is
+// being handed out, so a lane that refills reads its job at shared-memory latency.
+template <bool WITH_DESC>
+struct JobPool {
+    uint4* pool;                 // [96] per warp: job j = pool[3j .. 3j+2]; WITH_DESC: [96..127] = descriptors
+    uint4 nx0, nx1, nx2, nxd;    // this lane's pieces (lane, lane+32, lane+64) of the next block (+ its descriptor)
+    uint32_t base, used, count;  // current block: first item, items handed out, items it holds
+    uint32_t next_base, next_count;
+
+    __device__ __forceinline__ void fetch_next(uint32_t* counter, const uint4* jobs_u4, const uint4* descs, uint32_t n_items, uint32_t lane) {
+        uint32_t nb = 0;
+        if (lane == 0) nb = atomicAdd(counter, 32u);
+        nb = __shfl_sync(0xffffffffu, nb, 0);
+        next_base = nb;
+        next_count = nb < n_items ? min(32u, n_items - nb) : 0u;
+        const uint4* src = jobs_u4 + (size_t)nb * 3u;
+        const uint32_t pieces = 3u * next_count;
+        if (lane < pieces) nx0 = __ldg(src + lane);
+        if (lane + 32u < pieces) nx1 = __ldg(src + lane + 32u);
+        if (lane + 64u < pieces) nx2 = __ldg(src + lane + 64u);
+        if (WITH_DESC && lane < next_count) nxd = __ldg(descs + nb + lane);
+    }
+    __device__ __forceinline__ void swap_in(uint32_t* counter, const uint4* jobs_u4, const uint4* descs, uint32_t n_items, uint32_t lane) {
+        __syncwarp();
+        pool[lane] = nx0; pool[lane + 32] = nx1; pool[lane + 64] = nx2;
+        if (WITH_DESC) pool[lane + 96] = nxd;
+        __syncwarp();
+        base = next_base; count = next_count; used = 0;
+        if (count) fetch_next(counter, jobs_u4, descs, n_items, lane);
+    }
+    __device__ __forceinline__ void init(uint4* smem, uint32_t* counter, const uint4* jobs_u4, const uint4* descs, uint32_t n_items, uint32_t lane) {
+        pool = smem;
+        nx0 = nx1 = nx2 = nxd = make_uint4(0, 0, 0, 0);
+        base = used = count = 0;
+        fetch_next(counter, jobs_u4, descs, n_items, lane);
+        swap_in(counter, jobs_u4, descs, n_items, lane);
+    }
+    // Lanes in `need` draw jobs in lane order; returns the pool slot of this lane or -1.  Warp-uniform bookkeeping.
+    __device__ __forceinline__ int draw(unsigned need, bool wants, uint32_t lane) {
+        const uint32_t idx = used + (uint32_t)__popc(need & ((1u << lane) - 1u));
+        const int slot = (wants && idx < count) ? (int)idx : -1;
+        used = min(count, used + (uint32_t)__popc(need));
+        return slot;
+    }
+    __device__ __forceinline__ bool empty() const { return used >= count; }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// big_values: one pair per step, four steps (one 16-byte chunk) per trip, lanes refill at trip boundaries.
+// When a lane is through with its pairs it leaves the count1 kernel everything that one needs in the job itself:
+// the bit position, the bit window and the partial chunk it has to continue in.
+// Dynamic shared memory: LUT | WARPS job pools (96 x 16 B) | WARPS word rings (kRingWords x 32 x 4 B)
+// ---------------------------------------------------------------------------------------------------------------
+template <int K, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) l3_huff_big_kernel(BatchParams p, uint32_t* counter) {
+    extern __shared__ __align__(16) uint32_t s_lut[];
+    for (uint32_t i = threadIdx.x; i < p.t.huff32_entries; i += blockDim.x) s_lut[i] = p.t.huff32[i];
+    __syncthreads();
+    const uint32_t lut = smem_addr(s_lut);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_items = (uint32_t)(p.grch_hi - p.grch_lo);
+    const uint32_t* const blob32 = reinterpret_cast<const uint32_t*>(p.blob);
+    HuffJob* const jobs = p.jobs + p.grch_lo;
+    uint4* const is_base = p.is + p.grch_lo * kIsChunks;
+    uint32_t* const s_after_lut = s_lut + ((p.t.huff32_entries + 3u) & ~3u);
+
+    BitWindow bw;
+    bw.words = blob32; bw.nwords = 1; bw.pos = 0; bw.w0 = bw.w1 = 0; bw.wn = bw.ready = bw.filled = 0;
+    bw.ring = smem_addr(s_after_lut + WARPS * 96 * 4 + warp * (kRingWords * 32) + lane);
+    uint32_t item = 0, widx = 0, bvw = 0, nbw = 0, r2w = 0, par1 = 0, par2 = 0;
+    uint32_t cur_base = lut, cur_sh = 31, cur_lin = 0;   // current region's book: LUT address, 32 - root bits, linbits
+    bool have = false;
+    const uint4* const jobs_u4 = reinterpret_cast<const uint4*>(jobs);
+    JobPool<false> jp;
+    jp.init(reinterpret_cast<uint4*>(s_after_lut) + warp * 96, counter, jobs_u4, nullptr, n_items, lane);
+
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !have);
+        if (__popc(need) >= K && !jp.empty()) {
+            cp_async_wait_all();   // nothing of a finished job may still be landing in a ring that is about to be re-primed
+            const int slot = jp.draw(need, !have, lane);
+            if (slot >= 0) {
+                const uint4 a = jp.pool[3 * slot], b = jp.pool[3 * slot + 1], w = jp.pool[3 * slot + 2];
+                item = jp.base + (uint32_t)slot;
+                have = true;
+                bvw = b.w & 0x3FFu;
+                widx = 0;
+                cur_base = lut + ((b.x & 0xFFFFu) << 2); cur_sh = (b.x >> 16) & 31u; cur_lin = b.x >> 24;
+                par1 = b.y; par2 = b.z;
+                nbw = (b.w >> 10) & 0x3FFu;
+                r2w = (b.w >> 20) & 0x3FFu;
+                bw.open(blob32 + a.x, a.y, a.z, w);
+            }
+            if (jp.empty()) jp.swap_in(counter, jobs_u4, nullptr, n_items, lane);   // the next block (none left: count = 0)
+        }
+        if (!__any_sync(0xffffffffu, have)) {
+            if (jp.empty()) break;
+            continue;
+        }
+        bw.top_up(have);
+
+        const bool act = have;
+        const uint32_t chunk = widx >> 2;
+        uint32_t q[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t pk = 0;
+            if (act && widx < bvw) {
+                if (widx >= nbw) {   // region change (at most twice per granule-channel)
+                    const bool one = widx < r2w;
+                    const uint32_t par = one ? par1 : par2;
+                    cur_base = lut + ((par & 0xFFFFu) << 2); cur_sh = (par >> 16) & 31u; cur_lin = par >> 24;
+                    nbw = one ? r2w : 0x7FFFFFFFu;
+                }
+                const uint32_t bits = bw.peek32();
+                uint32_t e = lds32(cur_base + ((bits >> cur_sh) << 2));
+                // codes longer than the root table: walk the sub-tables inside the same 32-bit window (the longest
+                // code is 19 bits, plus two sign bits)
+                uint32_t used = 0;
+                while ((int32_t)e < 0) {
+                    used += (e >> 22) & 31u;
+                    e = lds32(cur_base + (((e & 0xFFFFu) + __funnelshift_r(bits << used, 0u, e >> 16)) << 2));
+                }
+                if (e & 0x40000000u) {      // linbits escapes (minimp3.d:805-813), out of line
+                    int a0 = (int)(e & 15u), a1 = (int)((e >> 16) & 15u);
+                    bw.advance(used + ((e >> 8) & 15u));
+                    const uint32_t b = bw.peek32();   // linbits, sign, linbits, sign: at most 28 bits
+                    uint32_t n = 0;
+                    if (a0 == 15) { a0 += (int)(b >> (32u - cur_lin)); n = cur_lin; }
+                    if (a0) { if ((b << n) >> 31) a0 = -a0; n++; }
+                    if (a1 == 15) { a1 += (int)((b << n) >> (32u - cur_lin)); n += cur_lin; }
+                    if (a1) { if ((b << n) >> 31) a1 = -a1; n++; }
+                    bw.advance(n);
+                    pk = __byte_perm((uint32_t)a0, (uint32_t)a1, 0x5410);
+                } else {
+                    // the code ends `used + len` bits into the window; the sign bits of the non-zero values follow
+                    const uint32_t sb = __funnelshift_l(0u, bits << used, e >> 8);   // bits << (used + len)
+                    const uint32_t s0 = (sb >> 31) & (e >> 24);                     // sign of a0 if a0 != 0
+                    const uint32_t sb1 = __funnelshift_l(0u, sb, e >> 24);           // skip that bit if it was taken
+                    const uint32_t s1 = (sb1 >> 31) & (e >> 15) & 1u;               // sign of a1 if a1 != 0
+                    const uint32_t inc = s0 | (s1 << 16);
+                    pk = ((e & 0x000F000Fu) ^ (inc * 0xFFFFu)) + inc;                // negate the flagged halves (never zero)
+                    bw.advance(used + ((e >> 4) & 15u));                             // code + sign bits in one step
+                }
+                widx++;
+            }
+            q[k] = pk;
+        }
+        if (act) {
+            is_base[(uint64_t)item * kIsChunks + chunk] = make_uint4(q[0], q[1], q[2], q[3]);
+            if (widx >= bvw) {
+                uint4* jw = reinterpret_cast<uint4*>(jobs + item);
+                reinterpret_cast<uint32_t*>(jw)[2] = bw.pos;
+                jw[1] = make_uint4(q[0], q[1], q[2], q[3]);   // the chunk count1 continues in (only used when bvw & 3)
+                jw[2] = bw.close();
+                have = false;
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// count1: one quad per step; output words go through a per-lane ring in shared memory because a quad region starts
+// at any pair index (big_values is not a multiple of four pairs)
+// ---------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128) l3_huff_c1_kernel(BatchParams p, uint32_t* counter) {
+    __shared__ uint16_t s_code[128];
+    __shared__ uint2 s_val[256];
+    __shared__ uint32_t s_ring[4][8][32];
+    __shared__ uint32_t s_words[4][kRingWords][32];
+    __shared__ uint4 s_pool[4][128];
+    for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) s_code[i] = p.t.c1code[i];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_val[i] = p.t.c1val[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* const ring = &s_ring[warp][0][lane];   // slot k of this lane: ring[k * 32]
+    const uint32_t n_items = (uint32_t)(p.grch_hi - p.grch_lo);
+    const uint32_t* const blob32 = reinterpret_cast<const uint32_t*>(p.blob);
+    const HuffJob* const jobs = p.jobs + p.grch_lo;
+    const uint4* const descs = reinterpret_cast<const uint4*>(p.grch + p.grch_lo);
+    uint4* const is_base = p.is + p.grch_lo * kIsChunks;
+    uint8_t* const sf_base = p.sf + p.grch_lo * kSfRecBytes;
+
+    BitWindow bw;
+    bw.words = blob32; bw.nwords = 1; bw.pos = 0; bw.w0 = bw.w1 = 0; bw.wn = bw.ready = bw.filled = 0;
+    bw.ring = smem_addr(&s_words[warp][0][lane]);
+    uint32_t item = 0, widx = 0, limit = 0, cbase = 0;
+    bool have = false, fin = false;
+    const uint4* const jobs_u4 = reinterpret_cast<const uint4*>(jobs);
+    JobPool<true> jp;
+    jp.init(&s_pool[warp][0], counter, jobs_u4, descs, n_items, lane);
+
+    auto flush = [&](uint32_t chunk) {
+        const uint32_t* r = ring + (chunk & 1u) * 128u;
+        is_base[(uint64_t)item * kIsChunks + chunk] = make_uint4(r[0], r[32], r[64], r[96]);
+    };
+
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !have);
+        if (__popc(need) >= K && !jp.empty()) {
+            cp_async_wait_all();   // nothing of a finished job may still be landing in a ring that is about to be re-primed
+            const int slot = jp.draw(need, !have, lane);
+            if (slot >= 0) {
+                const uint4 a = jp.pool[3 * slot], part = jp.pool[3 * slot + 1], w = jp.pool[3 * slot + 2];
+                const uint4 dsc = jp.pool[96 + slot];
+                item = jp.base + (uint32_t)slot;
+                have = true;
+                fin = false;
+                widx = (dsc.y >> 12) & 0x1FFu;                 // big_values, in pairs
+                limit = a.w;
+                cbase = ((dsc.z >> 26) & 1u) * 64u;            // count1_table
+                bw.open(blob32 + a.x, a.y, a.z, w);
+                if (widx & 3u) {   // the big_values kernel left a partial chunk: continue inside it
+                    uint32_t* r = ring + (widx & 4u) * 32u;
+                    r[0] = part.x; r[32] = part.y; r[64] = part.z; r[96] = part.w;
+                }
+            }
+            if (jp.empty()) jp.swap_in(counter, jobs_u4, descs, n_items, lane);
+        }
+        if (!__any_sync(0xffffffffu, have)) {
+            if (jp.empty()) break;
+            continue;
+        }
+        bw.top_up(have);
+#pragma unroll 2
+        for (int k = 0; k < 4; k++) {
+            if (have && !fin) {
+                const uint32_t bits = bw.peek32();
+                const uint32_t e = s_code[cbase + (bits >> 26)];
+                const uint32_t len = e & 15u;
+                // the limit is tested after the code and before the signs (minimp3.d:866); the band terminator before
+                // each half of the quad (minimp3.d:873, 876)
+                if (bw.pos + len > limit || widx >= 288u) {
+                    fin = true;
+                } else {
+                    const uint32_t sb = bits << len;
+                    const uint2 v = s_val[(e & 0xF0u) | (sb >> 28)];
+                    const uint32_t w0i = widx;
+                    ring[(w0i & 7u) * 32u] = v.x;
+                    widx++;
+                    if (widx < 288u) {
+                        ring[(widx & 7u) * 32u] = v.y;
+                        widx++;
+                    }
+                    if ((widx ^ w0i) & ~3u) flush(w0i >> 2);
+                    bw.advance(e >> 8);
+                }
+            }
+        }
+        if (have && fin) {   // once per trip for all the lanes that ended in it
+            if (widx & 3u) {   // pad the last chunk with zeros
+                for (uint32_t k = widx & 3u; k < 4; k++) ring[((widx & 4u) + k) * 32u] = 0u;
+                flush(widx >> 2);
+            }
+            const uint32_t chunks = (widx + 3u) >> 2;
+            *reinterpret_cast<uint16_t*>(sf_base + (uint64_t)item * kSfRecBytes + 80) = (uint16_t)chunks;
+            if (p.zero_fill)
+                for (uint32_t c = chunks; c < (uint32_t)kIsChunks; c++) is_base[(uint64_t)item * kIsChunks + c] = make_uint4(0, 0, 0, 0);
+            have = false;
+        }
+    }
+    cp_async_wait_all();
+}
+
+void upload_entropy_constants();
+
+template <int K>
+static void launch_big(const BatchParams& p, uint32_t* cnt, uint64_t n, int sms, cudaStream_t s) {
+    constexpr int WARPS = 8;   // eight warps share one copy of the LUT: more resident warps per SM (the kernel is latency-bound)
+    static int occ = 0;
+    const size_t smem = (size_t)((p.t.huff32_entries + 3u) & ~3u) * 4 + WARPS * (96 * sizeof(uint4) + kRingWords * 32 * 4);
+    if (!occ) {
+        cudaFuncSetAttribute(l3_huff_big_kernel<K, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, l3_huff_big_kernel<K, WARPS>, 32 * WARPS, smem);
+        if (getenv("L3B_HUFF_OCC")) occ = atoi(getenv("L3B_HUFF_OCC"));
+        occ = std::max(1, occ);
+    }
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 32 * WARPS - 1) / (32 * WARPS), (uint64_t)sms * occ);
+    l3_huff_big_kernel<K, WARPS><<<blocks, 32 * WARPS, smem, s>>>(p, cnt);
+}
+
+int launch_entropy_v4(const BatchParams& p, int sub, cudaStream_t s) {
+    if (p.grch_hi <= p.grch_lo) return 0;
+    static bool configured = false;
+    static int k_big = 8, k_c1 = 8, occ_c1 = 4;   // count1: measured fastest at 4 CTAs per SM (2: 3.4 ms, 4: 2.4, 6: 2.7, 10: 3.1)
+    if (!configured) {
+        if (getenv("L3B_HUFF_K")) k_big = k_c1 = atoi(getenv("L3B_HUFF_K"));
+        if (getenv("L3B_HUFF_K_C1")) k_c1 = atoi(getenv("L3B_HUFF_K_C1"));
+        if (getenv("L3B_HUFF_OCC_C1")) occ_c1 = std::max(1, atoi(getenv("L3B_HUFF_OCC_C1")));
+        configured = true;
+    }
+    const uint64_t n = p.grch_hi - p.grch_lo;
+    l3_scf_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned blocks_c1 = (unsigned)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * occ_c1);
+    uint32_t* cnt = p.counters + 2 * sub;
+    switch (k_big) {
+    case 1: launch_big<1>(p, cnt, n, sms, s); break;
+    case 2: launch_big<2>(p, cnt, n, sms, s); break;
+    case 4: launch_big<4>(p, cnt, n, sms, s); break;
+    case 16: launch_big<16>(p, cnt, n, sms, s); break;
+    default: launch_big<8>(p, cnt, n, sms, s); break;
+    }
+    switch (k_c1) {
+    case 1: l3_huff_c1_kernel<1><<<blocks_c1, 128, 0, s>>>(p, cnt + 1); break;
+    case 2: l3_huff_c1_kernel<2><<<blocks_c1, 128, 0, s>>>(p, cnt + 1); break;
+    case 4: l3_huff_c1_kernel<4><<<blocks_c1, 128, 0, s>>>(p, cnt + 1); break;
+    case 16: l3_huff_c1_kernel<16><<<blocks_c1, 128, 0, s>>>(p, cnt + 1); break;
+    default: l3_huff_c1_kernel<8><<<blocks_c1, 128, 0, s>>>(p, cnt + 1); break;
+    }
+    return 3;
+}
+
+}  // namespace l3b

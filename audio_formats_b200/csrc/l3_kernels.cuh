@@ -36,12 +36,31 @@ struct DeviceTables {
     uint16_t huff_base[18];     // books 0..14, 15 = all-zero book, 16/17 = count1 A/B
     uint8_t huff_root[18];
     const uint8_t* count1;      // [2][64]
+    const uint32_t* huff32;     // HuffLut32::entries
+    uint32_t huff32_entries;
+    uint32_t huff32_base[16];   // books 0..14, 15 = all-zero book
+    uint8_t huff32_root[16];
+    const uint16_t* c1code;     // [2][64]
+    const uint2* c1val;         // [256]
     const uint8_t* sfb_of_pair; // [8][3][288]
     const uint8_t* sfb_width;   // [8][3][40]
     const uint16_t* sfb_start;  // [8][3][40]
     const uint16_t* perm;       // [8][2][576]
     const float* pow43;         // [129]
     const float* win;           // [240]  L3_WIN layout
+};
+
+// One Huffman job per granule-channel (48 bytes = three 16-byte loads, none depending on another): written by the
+// scalefactor kernel for the big_values kernel, which in turn leaves the count1 kernel its bit position, its bit
+// window and (in place of `par`/`misc`) the partial 16-byte chunk of output that the quads continue in.
+struct __align__(16) HuffJob {
+    uint32_t word_base;   // first 32-bit word of the stream's main data in the batch blob
+    uint32_t nwords;      // words readable from there (the pad words after the stream included)
+    uint32_t pos;         // bit position (relative to the stream's main data) where decoding continues
+    uint32_t limit;       // bit_start + part2_3_length (minimp3.d:1201)
+    uint32_t par[3];      // per region: LUT base | (32 - root_bits) << 16 | linbits << 24
+    uint32_t misc;        // big_values (pairs) | region1 start (pairs) << 10 | region2 start (pairs) << 20 | count1_table << 30
+    uint32_t w[4];        // the four words from the one holding bit `pos`: two big-endian, two in memory byte order
 };
 
 struct BatchParams {
@@ -55,6 +74,8 @@ struct BatchParams {
     float* pcm;
     uint64_t grch_lo, grch_hi;  // granule-channel range the entropy kernel covers in this launch
     int zero_fill;   // entropy kernel writes all 72 chunks (tap mode)
+    HuffJob* jobs;        // [n_grch]
+    uint32_t* counters;   // work-distribution counters of the Huffman kernels: 2 per sub-batch, zeroed before every run
     DeviceTables t;
 };
 
@@ -66,8 +87,11 @@ template <int NCH, int WARPS>
 __global__ void l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles);
 
 void launch_entropy(const BatchParams& p, cudaStream_t s);
+// lane-decoupled entropy path: scalefactor kernel, big_values kernel, count1 kernel (l3_entropy.cu); returns launches
+int launch_entropy_v4(const BatchParams& p, int sub, cudaStream_t s);
 void launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
                     uint32_t n_mono, cudaStream_t s, cudaEvent_t ev_mid);
 void upload_constants();
+void upload_entropy_constants();
 
 }  // namespace l3b
