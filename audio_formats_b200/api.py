@@ -8,6 +8,7 @@ getLengthInFrames, getSamplerate, isError, errorMessage -- plus the batch entry 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Sequence
 
@@ -69,10 +70,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not _LIB_PATH.exists():
-        raise L3BError(E_NOGPU, f"{_LIB_PATH} is missing: run `python -m audio_formats_b200.build` "
+    path = Path(os.environ["L3B_LIB"]) if os.environ.get("L3B_LIB") else _LIB_PATH   # L3B_LIB: an experimental build (A/B runs)
+    if not path.exists():
+        raise L3BError(E_NOGPU, f"{path} is missing: run `python -m audio_formats_b200.build` "
                                 "(there is no CPU fallback)")
-    L = C.CDLL(str(_LIB_PATH))
+    L = C.CDLL(str(path))
     vp, u8p = C.c_void_p, C.c_char_p
     sig = {
         "l3b_device_count": (C.c_int, []),

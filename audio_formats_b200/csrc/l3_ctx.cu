@@ -43,6 +43,7 @@ struct l3b_resident {
     float* d_pcm = nullptr;
     Tile* d_tiles[2] = {nullptr, nullptr};  // [0] stereo, [1] mono
     HuffJob* d_jobs = nullptr;              // one per granule-channel, written by the scalefactor kernel
+    uint32_t* d_group_stream = nullptr;     // stream index of granule-channel 128 k, for every k (search hint)
     uint32_t* d_counters = nullptr;         // 2 per sub-batch: item counters of the two Huffman kernels
     uint32_t n_tiles[2] = {0, 0};
     uint64_t n_grch = 0, pcm_floats = 0;
@@ -186,6 +187,7 @@ void l3b_batch_free(l3b_ctx_t* c, l3b_resident_t* r) {
     cudaFree(r->d_tiles[0]);
     cudaFree(r->d_tiles[1]);
     cudaFree(r->d_jobs);
+    cudaFree(r->d_group_stream);
     cudaFree(r->d_counters);
     delete r;
 }
@@ -269,13 +271,14 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
         CU_TRY_R(cudaMalloc(&r->d_blob, r->cap_blob));
     }
     if (b->n_grch > r->cap_grch || !r->d_grch) {
-        cudaFree(r->d_grch); cudaFree(r->d_is); cudaFree(r->d_sf); cudaFree(r->d_jobs);
-        r->d_grch = nullptr; r->d_is = nullptr; r->d_sf = nullptr; r->d_jobs = nullptr;
+        cudaFree(r->d_grch); cudaFree(r->d_is); cudaFree(r->d_sf); cudaFree(r->d_jobs); cudaFree(r->d_group_stream);
+        r->d_grch = nullptr; r->d_is = nullptr; r->d_sf = nullptr; r->d_jobs = nullptr; r->d_group_stream = nullptr;
         r->cap_grch = std::max<uint64_t>(1, grow(b->n_grch));
         CU_TRY_R(cudaMalloc(&r->d_grch, r->cap_grch * sizeof(l3b_grch_desc_t)));
         CU_TRY_R(cudaMalloc(&r->d_is, r->cap_grch * kIsChunks * sizeof(uint4)));
         CU_TRY_R(cudaMalloc(&r->d_sf, r->cap_grch * kSfRecBytes));
         CU_TRY_R(cudaMalloc(&r->d_jobs, r->cap_grch * sizeof(HuffJob)));
+        CU_TRY_R(cudaMalloc(&r->d_group_stream, (r->cap_grch / 128 + 2) * sizeof(uint32_t)));
     }
     if (!r->d_counters) CU_TRY_R(cudaMalloc(&r->d_counters, 2 * l3b_ctx::kMaxSubs * sizeof(uint32_t)));
     if (b->pcm_floats > r->cap_pcm || !r->d_pcm) {
@@ -307,6 +310,16 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     for (int k = 0; k < 2; k++)
         if (r->n_tiles[k])
             CU_TRY_R(cudaMemcpyAsync(r->d_tiles[k], tiles[k].data(), tiles[k].size() * sizeof(Tile), cudaMemcpyHostToDevice, c->stream));
+    std::vector<uint32_t> group_stream((size_t)(b->n_grch / 128 + 1));
+    {
+        uint32_t si = 0;
+        for (size_t g = 0; g < group_stream.size(); g++) {
+            const uint64_t gi = (uint64_t)g * 128;
+            while (si + 1 < b->n_streams && b->streams[si + 1].first_grch <= gi) si++;
+            group_stream[g] = si;
+        }
+    }
+    CU_TRY_R(cudaMemcpyAsync(r->d_group_stream, group_stream.data(), group_stream.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     CU_TRY_R(cudaStreamSynchronize(c->stream));  // the host tile vectors go out of scope
 #undef CU_TRY_R
     BatchParams& p = r->params;
@@ -319,6 +332,7 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     p.sf = r->d_sf;
     p.pcm = r->d_pcm;
     p.jobs = r->d_jobs;
+    p.group_stream = r->d_group_stream;
     p.counters = r->d_counters;
     p.zero_fill = b->taps ? 1 : 0;
     p.t = c->t;
@@ -358,19 +372,13 @@ int l3b_batch_run(l3b_ctx_t* c, l3b_resident_t* r) {
     CU_TRY(c, cudaEventRecord(ev[0], A));
     CU_TRY(c, cudaStreamWaitEvent(B, ev[0], 0));   // uploads on A are complete before anything on B starts
     int launches = 0;
-    static const bool entropy_v3 = getenv("L3B_ENTROPY") && !strcmp(getenv("L3B_ENTROPY"), "v3");   // A/B switch: the lockstep kernel
-    if (!entropy_v3) CU_TRY(c, cudaMemsetAsync(r->d_counters, 0, 2 * l3b_ctx::kMaxSubs * sizeof(uint32_t), A));
+    CU_TRY(c, cudaMemsetAsync(r->d_counters, 0, 2 * l3b_ctx::kMaxSubs * sizeof(uint32_t), A));
     for (int i = 0; i < ns; i++) {
         const l3b_resident::Sub& sb = r->subs[i];
         BatchParams p = r->params;
         p.grch_lo = sb.grch_lo;
         p.grch_hi = sb.grch_hi;
-        if (entropy_v3) {
-            launch_entropy(p, A);
-            launches += sb.grch_hi > sb.grch_lo;
-        } else {
-            launches += launch_entropy_v4(p, i, A);
-        }
+        launches += launch_entropy_v4(p, i, A);
         cudaEvent_t* se = ev + 3 + 3 * i;
         CU_TRY(c, cudaEventRecord(se[0], A));
         CU_TRY(c, cudaStreamWaitEvent(B, se[0], 0));   // granule kernels of sub-batch i wait for its spectra only

@@ -32,6 +32,7 @@ __constant__ uint8_t e_lsf_mod[24];
 __constant__ uint8_t e_preamp[10];
 __constant__ uint8_t e_linbits[32];
 __constant__ int8_t e_sel2book[32];
+__constant__ float e_expfrac[4];
 
 void upload_entropy_constants() {
     cudaMemcpyToSymbol(e_partitions, L3_SCF_PARTITIONS, sizeof e_partitions);
@@ -40,42 +41,72 @@ void upload_entropy_constants() {
     cudaMemcpyToSymbol(e_preamp, L3_PREAMP, sizeof e_preamp);
     cudaMemcpyToSymbol(e_linbits, L3_LINBITS, sizeof e_linbits);
     cudaMemcpyToSymbol(e_sel2book, L3_SEL2BOOK, sizeof e_sel2book);
+    cudaMemcpyToSymbol(e_expfrac, L3_EXPFRAC, sizeof e_expfrac);
 }
 
 namespace {
 
-// MSB-first bit reader over the 32-bit words of a stream's main data (scalefactor fields only).
+// MSB-first bit reader over the 32-bit words of a stream's main data (scalefactor fields only).  Four words are
+// loaded up front (independent loads, one wait) and shifted through registers; further words are fetched two
+// crossings before they are needed.
 struct ScfReader {
     const uint32_t* words;
-    uint32_t nwords, pos;
+    uint32_t nwords, pos, w0, w1, w2, w3, wn;
     // nwords counts the 16 zero pad bytes that follow every stream, so clamping the index makes reads past the end
     // return zero bits without a branch
     __device__ __forceinline__ uint32_t ldw(uint32_t i) const { return __byte_perm(__ldg(words + min(i, nwords - 1)), 0, 0x0123); }
-    __device__ __forceinline__ uint32_t peek_at(uint32_t at, int n) const {   // 1 <= n <= 16
+    __device__ __forceinline__ void open(uint32_t bitpos) {
+        pos = bitpos;
+        const uint32_t wi = bitpos >> 5;
+        w0 = ldw(wi); w1 = ldw(wi + 1); w2 = ldw(wi + 2); w3 = ldw(wi + 3);
+        wn = wi + 4;
+    }
+    __device__ __forceinline__ uint32_t peek_at(uint32_t at, int n) const {   // random access, 1 <= n <= 16
         const uint32_t wi = at >> 5;
         return __funnelshift_l(ldw(wi + 1), ldw(wi), at) >> (32 - n);
     }
-    __device__ __forceinline__ uint32_t get(int n) { const uint32_t v = peek_at(pos, n); pos += (uint32_t)n; return v; }
+    __device__ __forceinline__ uint32_t get(int n) {   // 1 <= n <= 16
+        const uint32_t v = __funnelshift_l(w1, w0, pos) >> (32 - n);
+        const uint32_t np = pos + (uint32_t)n;
+        if ((np ^ pos) & ~31u) { w0 = w1; w1 = w2; w2 = w3; w3 = ldw(wn); wn++; }
+        pos = np;
+        return v;
+    }
 };
 
-__device__ __forceinline__ uint32_t find_stream(const l3b_stream_desc_t* streams, uint32_t n, uint64_t gi) {
-    uint32_t lo = 0, hi = n - 1;
-    while (lo < hi) {  // last stream with first_grch <= gi
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (streams[mid].first_grch <= gi) lo = mid; else hi = mid - 1;
-    }
-    return lo;
+// L3_ldexp_q2 (minimp3.d:646-657): y * 2^(-exp_q2/4) by repeated multiplication, same rounding steps.
+// (float)((1 << 30) >> k) is the power of two 2^(30-k), 0 <= k <= 30: built from its exponent bits instead of an
+// integer shift + conversion; g_expfrac[e & 3] is picked from registers (a lane-varying constant-bank index would
+// be serialised).
+__device__ __forceinline__ float ldexp_q2(float y, int exp_q2) {
+    const float f0 = e_expfrac[0], f1 = e_expfrac[1], f2 = e_expfrac[2], f3 = e_expfrac[3];
+    int e;
+    do {
+        e = exp_q2 < 120 ? exp_q2 : 120;
+        const float frac = (e & 2) ? ((e & 1) ? f3 : f2) : ((e & 1) ? f1 : f0);
+        const float pw = __int_as_float((127 + 30 - (e >> 2)) << 23);
+        y = __fmul_rn(y, __fmul_rn(frac, pw));
+    } while ((exp_q2 -= e) > 0);
+    return y;
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
-// Scalefactors + job setup: one thread per granule-channel
+// Scalefactors + band gains + job setup: one thread per granule-channel
+static_assert(kSfRecBytes == 256 && sizeof(HuffJob) == 48, "the staging rows of l3_scf_kernel assume these sizes");
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
-    const uint64_t gi = p.grch_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= p.grch_hi) return;
-    const uint32_t si = find_stream(p.streams, p.n_streams, gi);
+    // per warp: 32 records of 17 x 16 bytes (one spare: conflict-free 16-byte rows), written out as one contiguous run
+    extern __shared__ __align__(16) uint4 s_stage[];
+    const uint32_t lane = threadIdx.x & 31;
+    uint4* const wstage = s_stage + (threadIdx.x >> 5) * (32 * 17);
+    const uint64_t g_first = p.grch_lo + (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);   // first of this warp
+    if (g_first >= p.grch_hi) return;
+    const uint32_t n_live = (uint32_t)min((uint64_t)32, p.grch_hi - g_first);
+    const uint64_t gi = min(g_first + lane, p.grch_hi - 1);   // tail lanes shadow the last granule-channel
+    uint32_t si = __ldg(p.group_stream + (g_first >> 7));   // a stream at or before ours: walk forward (usually 0 steps)
+    while (si + 1 < p.n_streams && p.streams[si + 1].first_grch <= gi) si++;
     const l3b_stream_desc_t* S = p.streams + si;
     const int nch = S->nch;
     const int ch = (int)((gi - S->first_grch) % (uint64_t)nch);
@@ -84,12 +115,12 @@ __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
     br.words = reinterpret_cast<const uint32_t*>(p.blob + S->maindata_off);
     br.nwords = (S->maindata_bytes >> 2) + 4;  // the batch blob keeps >= 16 zero bytes after each stream
     const Desc d = load_desc(p.grch + gi);
-    br.pos = d.bit_start;
+    br.open(d.bit_start);
 
     // ---------------- scalefactors (minimp3.d:613-644, 659-712) ----------------
-    uint32_t recw[kSfRecBytes / 4];
+    uint32_t recw[kSfGainOff / 4];
 #pragma unroll
-    for (int i = 0; i < kSfRecBytes / 4; i++) recw[i] = 0;
+    for (int i = 0; i < kSfGainOff / 4; i++) recw[i] = 0;
     uint8_t* const rec = reinterpret_cast<uint8_t*>(recw);   // thread-local staging of the record (local memory, 96 B)
     const int kind = d.kind();
     const int n_long = kind == 0 ? 22 : (kind == 1 ? 0 : (mpeg1 ? 8 : 6));
@@ -170,9 +201,28 @@ __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
         }
     }
     {
-        uint4* dst = reinterpret_cast<uint4*>(p.sf + gi * kSfRecBytes);
+        uint4* dst = wstage + lane * 17;
 #pragma unroll
-        for (int i = 0; i < kSfRecBytes / 16; i++) dst[i] = make_uint4(recw[4 * i], recw[4 * i + 1], recw[4 * i + 2], recw[4 * i + 3]);
+        for (int i = 0; i < kSfGainOff / 16; i++) dst[i] = make_uint4(recw[4 * i], recw[4 * i + 1], recw[4 * i + 2], recw[4 * i + 3]);
+        // ---------------- band gains (minimp3.d:714-719): scf[i] = 2^(gain_exp/4) * 2^(-(iscf[i] << shift)/4) ----------------
+        const bool ms_frame = (d.hdr_bits() & 0xE) == 0x6;   // HDR_IS_MS_STEREO: the 1/sqrt(2) of MS stereo is folded in here
+        const int n_sfb = kind == 0 ? 22 : (kind == 1 ? 39 : (mpeg1 ? 38 : 36));
+        const int gain_exp = d.global_gain() - 4 - 210 - (ms_frame ? 2 : 0);
+        const float gain = ldexp_q2(2048.0f, 44 - gain_exp);
+        float4* gdst = reinterpret_cast<float4*>(dst + kSfGainOff / 16);
+        for (int i4 = 0; i4 < 10; i4++) {
+            float g[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = 4 * i4 + k;
+                g[k] = i < n_sfb ? ldexp_q2(gain, (int)rec[i] << scf_shift) : 0.0f;
+            }
+            gdst[i4] = make_float4(g[0], g[1], g[2], g[3]);
+        }
+        __syncwarp();
+        uint4* out = reinterpret_cast<uint4*>(p.sf + g_first * kSfRecBytes);
+        for (uint32_t idx = lane; idx < n_live * (kSfRecBytes / 16); idx += 32) out[idx] = wstage[(idx >> 4) * 17 + (idx & 15)];
+        __syncwarp();
     }
 
     // ---------------- Huffman job ----------------
@@ -189,15 +239,14 @@ __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
     }
     j.misc = (uint32_t)d.big_values() | ((uint32_t)(d.region1_start() >> 1) << 10) | ((uint32_t)(d.region2_start() >> 1) << 20) |
              ((uint32_t)d.count1_table() << 30);
-    const uint32_t wi = br.pos >> 5;
-    uint4* jd = reinterpret_cast<uint4*>(p.jobs + gi);
+    uint4* jd = wstage + lane * 3;
     jd[0] = make_uint4(j.word_base, j.nwords, j.pos, j.limit);
     jd[1] = make_uint4(j.par[0], j.par[1], j.par[2], j.misc);
-    {   // the first four words of the bit window (the last two in memory byte order): no dependent load at refill
-        const uint32_t* w = br.words;
-        const uint32_t last = br.nwords - 1;
-        jd[2] = make_uint4(br.ldw(wi), br.ldw(wi + 1), __ldg(w + min(wi + 2, last)), __ldg(w + min(wi + 3, last)));
-    }
+    // the first four words of the bit window (the last two in memory byte order): no dependent load at refill
+    jd[2] = make_uint4(br.w0, br.w1, __byte_perm(br.w2, 0, 0x0123), __byte_perm(br.w3, 0, 0x0123));
+    __syncwarp();
+    uint4* jout = reinterpret_cast<uint4*>(p.jobs + g_first);
+    for (uint32_t idx = lane; idx < n_live * 3; idx += 32) jout[idx] = wstage[idx];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -576,7 +625,7 @@ int launch_entropy_v4(const BatchParams& p, int sub, cudaStream_t s) {
         configured = true;
     }
     const uint64_t n = p.grch_hi - p.grch_lo;
-    l3_scf_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+    l3_scf_kernel<<<(unsigned)((n + 127) / 128), 128, 4 * 32 * 17 * sizeof(uint4), s>>>(p);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

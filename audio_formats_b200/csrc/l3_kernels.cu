@@ -16,12 +16,6 @@ __constant__ float c_twid3[6];
 __constant__ float c_mdctw[36];
 __constant__ float c_sec[24];
 __constant__ float c_pan[14];
-__constant__ uint8_t c_partitions[84];
-__constant__ uint8_t c_scfc_decode[16];
-__constant__ uint8_t c_lsf_mod[24];
-__constant__ uint8_t c_preamp[10];
-__constant__ uint8_t c_linbits[32];
-__constant__ int8_t c_sel2book[32];
 
 void upload_constants() {
     cudaMemcpyToSymbol(c_expfrac, L3_EXPFRAC, sizeof c_expfrac);
@@ -31,284 +25,6 @@ void upload_constants() {
     cudaMemcpyToSymbol(c_mdctw, L3_MDCT_WINDOW, sizeof c_mdctw);
     cudaMemcpyToSymbol(c_sec, L3_SEC, sizeof c_sec);
     cudaMemcpyToSymbol(c_pan, L3_PAN, sizeof c_pan);
-    cudaMemcpyToSymbol(c_partitions, L3_SCF_PARTITIONS, sizeof c_partitions);
-    cudaMemcpyToSymbol(c_scfc_decode, L3_SCFC_DECODE, sizeof c_scfc_decode);
-    cudaMemcpyToSymbol(c_lsf_mod, L3_LSF_MOD, sizeof c_lsf_mod);
-    cudaMemcpyToSymbol(c_preamp, L3_PREAMP, sizeof c_preamp);
-    cudaMemcpyToSymbol(c_linbits, L3_LINBITS, sizeof c_linbits);
-    cudaMemcpyToSymbol(c_sel2book, L3_SEL2BOOK, sizeof c_sel2book);
-}
-
-// =====================================================================================================
-// Entropy kernel
-// =====================================================================================================
-
-// MSB-first reader over 32-bit words of the stream's main-data blob.  cache holds `nbits` valid bits,
-// left aligned; the next word to load is `next`.  Reads past the blob return zero bits.
-struct BitCursor {
-    const uint32_t* words;
-    uint32_t nwords, next, pos;
-    uint64_t cache;
-    int nbits;
-    // nwords counts the 16 zero pad bytes that follow every stream, so clamping the index makes reads past
-    // the end return zero bits without a branch
-    __device__ __forceinline__ uint32_t ldw(uint32_t i) const {
-        return __byte_perm(__ldg(words + min(i, nwords - 1)), 0, 0x0123);
-    }
-    __device__ __forceinline__ void init(const uint32_t* w, uint32_t nw, uint32_t bitpos) {
-        words = w; nwords = nw; pos = bitpos;
-        uint32_t wi = bitpos >> 5, off = bitpos & 31;
-        cache = (((uint64_t)ldw(wi) << 32) | ldw(wi + 1)) << off;
-        nbits = 64 - (int)off;
-        next = wi + 2;
-    }
-    __device__ __forceinline__ void refill() {
-        if (nbits <= 32) {
-            cache |= (uint64_t)ldw(next++) << (32 - nbits);
-            nbits += 32;
-        }
-    }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(cache >> (64 - n)); }  // 1..32
-    __device__ __forceinline__ void skip(int n) { cache <<= n; nbits -= n; pos += n; }
-    __device__ __forceinline__ uint32_t get(int n) {  // n >= 1
-        refill();
-        uint32_t v = peek(n);
-        skip(n);
-        return v;
-    }
-};
-
-__device__ __forceinline__ uint32_t peek_bits_at(const uint32_t* words, uint32_t nwords, uint32_t bitpos, int n) {
-    uint32_t wi = bitpos >> 5, off = bitpos & 31;
-    uint32_t a = wi < nwords ? __byte_perm(__ldg(words + wi), 0, 0x0123) : 0u;
-    uint32_t b = wi + 1 < nwords ? __byte_perm(__ldg(words + wi + 1), 0, 0x0123) : 0u;
-    uint64_t v = (((uint64_t)a << 32) | b) << off;
-    return (uint32_t)(v >> (64 - n));
-}
-
-__device__ __forceinline__ uint32_t find_stream(const l3b_stream_desc_t* streams, uint32_t n, uint64_t gi) {
-    uint32_t lo = 0, hi = n - 1;
-    while (lo < hi) {  // last stream with first_grch <= gi
-        uint32_t mid = (lo + hi + 1) >> 1;
-        if (streams[mid].first_grch <= gi) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
-__global__ void __launch_bounds__(128) l3_entropy_kernel(BatchParams p) {
-    extern __shared__ uint16_t s_lut[];  // huff entries, then 128 bytes of count1
-    for (uint32_t i = threadIdx.x; i < p.t.huff_entries; i += blockDim.x) s_lut[i] = p.t.huff[i];
-    __syncthreads();
-
-    uint64_t gi = p.grch_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = gi < p.grch_hi;
-    if (__all_sync(0xffffffffu, !live)) return;
-    if (!live) gi = p.grch_hi - 1;  // tail lanes of the last warp shadow its last granule-channel in lockstep
-    const uint32_t si = find_stream(p.streams, p.n_streams, gi);
-    const l3b_stream_desc_t* S = p.streams + si;
-    const int nch = S->nch;
-    const int ch = (int)((gi - S->first_grch) % (uint64_t)nch);
-    const bool mpeg1 = S->mpeg1 != 0;
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(p.blob + S->maindata_off);
-    const uint32_t nwords = (S->maindata_bytes >> 2) + 4;  // the batch blob keeps >= 16 zero bytes after each stream
-
-    const Desc d = load_desc(p.grch + gi);
-    BitCursor br;
-    br.init(words, nwords, d.bit_start);
-    const uint32_t limit = d.bit_start + (uint32_t)d.part23();
-
-    // ---------------- scalefactors (minimp3.d:613-644, 659-712) ----------------
-    uint8_t* rec = p.sf + gi * kSfRecBytes;
-    {
-        uint4 z = make_uint4(0, 0, 0, 0);
-        uint4* r4 = reinterpret_cast<uint4*>(rec);
-#pragma unroll
-        for (int i = 0; i < kSfRecBytes / 16; i++) r4[i] = z;
-    }
-    const int kind = d.kind();
-    const int n_long = kind == 0 ? 22 : (kind == 1 ? 0 : (mpeg1 ? 8 : 6));
-    const int n_short = kind == 0 ? 0 : (kind == 1 ? 39 : 30);
-    const uint8_t* part = c_partitions + 28 * (kind == 0 ? 0 : (kind == 2 ? 1 : 2));
-    const int scf_shift = d.scalefac_scale() + 1;
-    uint32_t slen = 0;  // four byte-sized lengths
-    int scfsi = d.scfsi();
-    const int istereo = d.hdr_bits() & 1;
-    if (mpeg1) {
-        int pp = c_scfc_decode[d.scalefac_compress() & 15];
-        uint32_t a = (uint32_t)(pp >> 2), b = (uint32_t)(pp & 3);
-        slen = a | (a << 8) | (b << 16) | (b << 24);
-    } else {
-        int ist = (istereo && ch) ? 1 : 0;
-        int sfc = d.scalefac_compress() >> ist;
-        int k = ist * 12;
-        for (;; k += 4) {
-            int modprod = 1;
-            slen = 0;
-#pragma unroll
-            for (int i = 3; i >= 0; i--) {
-                int m = c_lsf_mod[k + i];
-                slen |= (uint32_t)(sfc / modprod % m) << (8 * i);
-                modprod *= m;
-            }
-            sfc -= modprod;
-            if (sfc < 0) break;
-        }
-        part += k + 4;  // the reference's for-loop increments k once more before its exit test (minimp3.d:683-691)
-        scfsi = -16;
-    }
-    // granule-0 scalefactors for scfsi copies (MPEG-1 granule 1 only; both granules are long blocks then)
-    uint32_t g0_slen = 0, g0_bits = 0;
-    if (scfsi > 0 && d.second_granule() && gi >= S->first_grch + (uint64_t)nch) {
-        const Desc d0 = load_desc(p.grch + gi - nch);
-        int pp = c_scfc_decode[d0.scalefac_compress() & 15];
-        uint32_t a = (uint32_t)(pp >> 2), b = (uint32_t)(pp & 3);
-        g0_slen = a | (a << 8) | (b << 16) | (b << 24);
-        g0_bits = d0.bit_start;
-    } else if (scfsi > 0) {
-        scfsi = 0;  // no granule 0 to copy from
-    }
-    {
-        const int sbg_sh = 3 - scf_shift;
-        int n = 0;
-        uint32_t g0_off = g0_bits;
-        for (int i = 0; i < 4; i++) {
-            const int cnt = part[i];
-            if (!cnt) break;
-            const int bits = (slen >> (8 * i)) & 0xFF;
-            const int bits0 = (g0_slen >> (8 * i)) & 0xFF;
-            const bool copy = (scfsi & 8) != 0;
-            for (int k = 0; k < cnt; k++, n++) {
-                int s, ip;
-                if (copy) {
-                    s = bits0 ? (int)peek_bits_at(words, nwords, g0_off + (uint32_t)(k * bits0), bits0) : 0;
-                    ip = s;
-                } else if (!bits) {
-                    s = 0; ip = 0;
-                } else {
-                    s = (int)br.get(bits);
-                    ip = (scfsi < 0 && s == (1 << bits) - 1) ? 255 : s;
-                }
-                int adj = 0;
-                if (n_short) { if (n >= n_long) adj = d.subblock_gain((n - n_long) % 3) << sbg_sh; }
-                else if (d.preflag() && n >= 11 && n < 21) adj = c_preamp[n - 11];
-                rec[n] = (uint8_t)(s + adj);
-                rec[40 + n] = (uint8_t)ip;
-            }
-            g0_off += (uint32_t)(cnt * bits0);
-            scfsi *= 2;
-        }
-        for (int j = 0; j < 3 && n < 40; j++, n++) {  // scf[0] = scf[1] = scf[2] = 0 after the last partition
-            int adj = 0;
-            if (n_short) { if (n >= n_long && n < n_long + n_short) adj = d.subblock_gain((n - n_long) % 3) << sbg_sh; }
-            rec[n] = (uint8_t)adj;
-        }
-    }
-
-    // ---------------- Huffman (minimp3.d:748-883), values only ----------------
-    // One PAIR of values per step in every lane, four steps (one 16-byte chunk) per loop trip, so the lanes
-    // of a warp stay on the same straight-line code: big_values pairs use the region's book; a count1 quad
-    // is decoded as two consecutive pairs of 0/1 magnitudes (first half: code + v0,v1; second half: v2,v3
-    // from the saved flags, through the zero-length book).  Sign bits follow the same rule in both
-    // (minimp3.d:819, 874-878).
-    uint4* outp = p.is + gi * kIsChunks;
-    const int bv_end = 2 * d.big_values();
-    // per-region book parameters: base | root<<16 | linbits<<24
-    uint32_t par[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-        const int sel = d.table_select(r);
-        const int book = c_sel2book[sel] < 0 ? L3_NBOOKS : c_sel2book[sel];
-        par[r] = (uint32_t)p.t.huff_base[book] | ((uint32_t)p.t.huff_root[book] << 16) | ((uint32_t)c_linbits[sel] << 24);
-    }
-    const uint32_t par_c1 = (uint32_t)p.t.huff_base[L3_NBOOKS + 1 + d.count1_table()] | (6u << 16);
-    const uint32_t par_zero = (uint32_t)p.t.huff_base[L3_NBOOKS] | (1u << 16);
-
-    // 32-bit window over the bit stream: (w0:w1) are the words at wi, wi+1; pos is the absolute bit position
-    uint32_t pos = br.pos;
-    uint32_t wi = pos >> 5;
-    uint32_t w0 = br.ldw(wi), w1 = br.ldw(wi + 1);
-#define L3_PEEK32() __funnelshift_l(w1, w0, pos)
-#define L3_ADVANCE(n)                                                 \
-    do {                                                              \
-        pos += (uint32_t)(n);                                         \
-        if ((pos >> 5) != wi) { wi++; w0 = w1; w1 = br.ldw(wi + 1); } \
-    } while (0)
-
-    int idx = 0;
-    int nb = d.region1_start();      // next region boundary
-    uint32_t cur = par[0];
-    int reg = 0;
-    bool done = false;
-    uint32_t pend = 0;  // bit 2: second half of a quad pending; bits 0,1: its v2,v3 flags
-    const int r2 = d.region2_start();
-
-    auto decode_pair = [&]() -> uint32_t {
-        const bool in_big = idx < bv_end;
-        if (in_big && idx >= nb) {   // region change (at most twice per granule-channel)
-            reg = idx < r2 ? 1 : 2;
-            cur = par[reg];
-            nb = reg == 1 ? r2 : 576;
-        }
-        const bool second = !in_big && (pend & 4u);
-        const bool first = !in_big && !second;
-        const uint32_t pr = in_big ? cur : (second ? par_zero : par_c1);
-        const uint32_t base = pr & 0xFFFFu;
-        const int linbits = (int)(pr >> 24);
-        int w = (int)((pr >> 16) & 0xFF);
-        uint32_t bits = L3_PEEK32();
-        uint32_t e = s_lut[base + (bits >> (32 - w))];
-        while (e & 0x8000u) {  // codes longer than the root table (rare): walk the sub-tables
-            L3_ADVANCE(w);
-            w = (int)((e >> 12) & 7) + 1;
-            bits = L3_PEEK32();
-            e = s_lut[base + (e & 0xFFFu) + (bits >> (32 - w))];
-        }
-        // `bits` is the 32-bit window at pos; the (rest of the) code is its top `len` bits, the sign bits follow
-        const int len = (int)((e >> 8) & 15);
-        // quad bookkeeping: the limit is tested after the code and before the signs (minimp3.d:866), then the
-        // sfb terminator before each half (minimp3.d:873, 876)
-        const bool stop = (first && pos + (uint32_t)len > limit) || (!in_big && idx >= 576);
-        int a0 = second ? (int)(pend & 1u) : (int)(e & 15);
-        int a1 = second ? (int)((pend >> 1) & 1u) : (int)((e >> 4) & 15);
-        pend = first ? (4u | ((e >> 12) & 3u)) : 0u;
-        done = done || stop;
-        if (linbits && (a0 == 15 || a1 == 15)) {  // escapes (rare)
-            L3_ADVANCE(len);
-            if (a0 == 15) { a0 += (int)(L3_PEEK32() >> (32 - linbits)); L3_ADVANCE(linbits); }
-            { const int n0 = a0 != 0; const int sg = n0 & (int)(L3_PEEK32() >> 31); L3_ADVANCE(n0); a0 = sg ? -a0 : a0; }
-            if (a1 == 15) { a1 += (int)(L3_PEEK32() >> (32 - linbits)); L3_ADVANCE(linbits); }
-            { const int n1 = a1 != 0; const int sg = n1 & (int)(L3_PEEK32() >> 31); L3_ADVANCE(n1); a1 = sg ? -a1 : a1; }
-        } else {
-            const int n0 = a0 != 0, n1 = a1 != 0;
-            const uint32_t sb = bits << len;            // sign bits at the top (len + 2 <= 32 always)
-            const int s0 = n0 & (int)(sb >> 31);
-            const int s1 = n1 & (int)((sb << n0) >> 31);
-            L3_ADVANCE(len + n0 + n1);                  // one advance for code + signs
-            a0 = (a0 ^ -s0) + s0;
-            a1 = (a1 ^ -s1) + s1;
-        }
-        uint32_t pk = __byte_perm((uint32_t)a0, (uint32_t)a1, 0x5410);
-        if (done) pk = 0; else idx += 2;
-        return pk;
-    };
-
-    while (__any_sync(0xffffffffu, !done)) {
-        // `done` lanes keep running the same code into dead registers (their pos/idx no longer matter)
-        const int at = idx >> 3;
-        const bool was_done = done;
-        uint4 q;
-        q.x = decode_pair();
-        q.y = decode_pair();
-        q.z = decode_pair();
-        q.w = decode_pair();
-        if (!was_done && at < kIsChunks) outp[at] = q;
-    }
-#undef L3_PEEK32
-#undef L3_ADVANCE
-    int chunks = (idx + 7) >> 3;
-    if (p.zero_fill)
-        for (int c = chunks; c < kIsChunks; c++) outp[c] = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint16_t*>(rec + 80) = (uint16_t)chunks;
 }
 
 // =====================================================================================================
@@ -572,7 +288,6 @@ struct __align__(16) WarpSmem {
     uint4 st_is[NCH * kIsChunks];              // TMA-staged inputs of the next granule: quantised spectra,
     uint4 st_rec[NCH * kSfRecBytes / 16];      //   scalefactor records,
     uint4 st_desc[NCH];                        //   descriptors
-    float scf[NCH][40];
     uint8_t sfbpair[3][288];
     uint8_t ist[40];
     uint8_t smode[40];
@@ -693,24 +408,9 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             const uint8_t* rec0 = reinterpret_cast<const uint8_t*>(W.st_rec);
             const uint8_t* rec1 = rec0 + (NCH - 1) * kSfRecBytes;
 
-            // ---------------- band gains (minimp3.d:714-719) ----------------
-#ifndef L3B_EXP_SKIP_GAINS
-#pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                const Desc& d = c ? d1 : d0;
-                const uint8_t* rec = c ? rec1 : rec0;
-                const int kind = c ? kind1 : kind0;
-                const int n_sfb = kind == 0 ? 22 : (kind == 1 ? 39 : (mpeg1 ? 38 : 36));
-                const int gain_exp = d.global_gain() - 4 - 210 - (ms_frame ? 2 : 0);
-                const float gain = ldexp_q2(2048.0f, 44 - gain_exp);
-                const int scf_shift = d.scalefac_scale() + 1;
-                for (int i = lane; i < 40; i += 32) {
-                    float v = 0.0f;
-                    if (i < n_sfb) v = ldexp_q2(gain, (int)rec[i] << scf_shift);
-                    W.scf[c][i] = v;
-                }
-            }
-#endif
+            // band gains (minimp3.d:714-719) come ready-made in the scalefactor record (l3_scf_kernel)
+            const float* const scf0 = reinterpret_cast<const float*>(rec0 + kSfGainOff);
+            const float* const scf1 = reinterpret_cast<const float*>(rec1 + kSfGainOff);
             if (istereo)
                 for (int i = lane; i < 40; i += 32) W.ist[i] = rec1[40 + i];
             __syncwarp();
@@ -733,12 +433,12 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                         continue;
                     }
                     const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;   // chunks past nz_chunks were never written
-                    const float sa = W.scf[0][W.sfbpair[kind0][pi]];
+                    const float sa = scf0[W.sfbpair[kind0][pi]];
                     float a0 = requant(s_pow43, (int)(int16_t)(va & 0xFFFFu), sa);
                     float a1 = requant(s_pow43, (int)(int16_t)(va >> 16), sa);
                     if (NCH == 2) {
                         const uint32_t vb = (pi >> 2) < nch1 ? isw1[pi] : 0u;
-                        const float sb = W.scf[NCH - 1][W.sfbpair[kind1][pi]];
+                        const float sb = scf1[W.sfbpair[kind1][pi]];
                         float b0 = requant(s_pow43, (int)(int16_t)(vb & 0xFFFFu), sb);
                         float b1 = requant(s_pow43, (int)(int16_t)(vb >> 16), sb);
                         if (ms_now) {
@@ -1079,13 +779,6 @@ static void launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n
         configured = true;
     }
     l3_granule_kernel<NCH, WARPS><<<(n + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(p, tiles, n);
-}
-
-void launch_entropy(const BatchParams& p, cudaStream_t s) {
-    if (p.grch_hi <= p.grch_lo) return;
-    size_t smem = (size_t)((p.t.huff_entries + 7) & ~7u) * 2;
-    unsigned blocks = (unsigned)((p.grch_hi - p.grch_lo + 127) / 128);
-    l3_entropy_kernel<<<blocks, 128, smem, s>>>(p);
 }
 
 void launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,

@@ -21,9 +21,13 @@
 
 namespace l3b {
 
-constexpr int kSfRecBytes = 96;    // per granule-channel: iscf[40] ist_pos[40] nz_chunks(u16) pad
+constexpr int kSfRecBytes = 256;   // per granule-channel: iscf[40] ist_pos[40] nz_chunks(u16) pad[14] gains f32[40]
+constexpr int kSfGainOff = 96;     // byte offset of the 40 band gains (minimp3.d:714-719) inside the record
 constexpr int kIsChunks = 72;      // 576 int16 = 72 x 16 bytes
-constexpr int kTileGranules = 32;  // granules per CTA tile of the granule kernel (2-granule recompute halo)
+#ifndef L3B_TILE_GRANULES
+#define L3B_TILE_GRANULES 64
+#endif
+constexpr int kTileGranules = L3B_TILE_GRANULES;  // granules per warp tile of the granule kernel (2-granule recompute halo)
 constexpr int kXrStride = 608;     // spectrum buffer elements: 576 in natural layout / 32x19 in the padded layout
 
 struct Tile {
@@ -75,6 +79,7 @@ struct BatchParams {
     uint64_t grch_lo, grch_hi;  // granule-channel range the entropy kernel covers in this launch
     int zero_fill;   // entropy kernel writes all 72 chunks (tap mode)
     HuffJob* jobs;        // [n_grch]
+    const uint32_t* group_stream;   // [n_grch / 128 + 1] stream index of granule-channel 128 k (search hint)
     uint32_t* counters;   // work-distribution counters of the Huffman kernels: 2 per sub-batch, zeroed before every run
     DeviceTables t;
 };
@@ -82,11 +87,9 @@ struct BatchParams {
 constexpr int kGranuleWarpsStereo = 4;   // warps (= tiles) per CTA of the granule kernel; 16 warps resident per SM.
 constexpr int kGranuleWarpsMono = 4;     // 4-warp CTAs measured best (16: 33.7 ms, 8: 28.6 ms, 4: 27.2 ms on config 2)
 
-__global__ void l3_entropy_kernel(BatchParams p);
 template <int NCH, int WARPS>
 __global__ void l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles);
 
-void launch_entropy(const BatchParams& p, cudaStream_t s);
 // lane-decoupled entropy path: scalefactor kernel, big_values kernel, count1 kernel (l3_entropy.cu); returns launches
 int launch_entropy_v4(const BatchParams& p, int sub, cudaStream_t s);
 void launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
