@@ -424,7 +424,15 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 const uint32_t* isw1 = isw0 + (NCH - 1) * (kIsChunks * 4);
                 const bool ms_now = NCH == 2 && ms_frame && !istereo;
                 const int nz_hi = max(nch0, NCH == 2 ? nch1 : 0);   // chunks (8 coefficients) holding anything non-zero
-#pragma unroll 3
+                // Fast path without a branch per value: every lane looks its four values up in the mirrored table through
+                // an offset that is masked into the table (|v| <= 127 is what almost all values are), so the lookups of
+                // a trip are independent of each other.  Lanes holding a larger value note the trip in `bigmask` and redo
+                // it afterwards through the general path.
+                // byte offset of s_pow43[v + 128] for -128 <= v <= 127 is 4v + 512 = ((4v) & 0x3FC) ^ 0x200; any other v
+                // lands somewhere inside the table (and is redone below)
+                const char* const tab = reinterpret_cast<const char*>(s_pow43);
+                uint32_t bigmask = 0;
+#pragma unroll
                 for (int m = 0; m < 9; m++) {
                     const int pi = lane + 32 * m;
                     if (8 * m >= nz_hi) {   // warp-uniform: both channels are zero from here on (+0.0, like the memset grbuf)
@@ -433,14 +441,17 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                         continue;
                     }
                     const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;   // chunks past nz_chunks were never written
+                    const uint32_t vb = (NCH == 2 && (pi >> 2) < nch1) ? isw1[pi] : 0u;
                     const float sa = scf0[W.sfbpair[kind0][pi]];
-                    float a0 = requant(s_pow43, (int)(int16_t)(va & 0xFFFFu), sa);
-                    float a1 = requant(s_pow43, (int)(int16_t)(va >> 16), sa);
+                    const float sb = NCH == 2 ? scf1[W.sfbpair[kind1][pi]] : 0.0f;
+                    // a 16-bit value lies in [-128, 127] iff its bits 15..7 are all equal
+                    const uint32_t wide = ((va ^ (va << 1)) | (vb ^ (vb << 1))) & 0xFF00FF00u;
+                    bigmask |= (wide ? 1u : 0u) << m;
+                    float a0 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((((int)(va << 16) >> 14) & 0x3FC) ^ 0x200)), sa);
+                    float a1 = __fmul_rn(*reinterpret_cast<const float*>(tab + (((((int)va >> 16) << 2) & 0x3FC) ^ 0x200)), sa);
                     if (NCH == 2) {
-                        const uint32_t vb = (pi >> 2) < nch1 ? isw1[pi] : 0u;
-                        const float sb = scf1[W.sfbpair[kind1][pi]];
-                        float b0 = requant(s_pow43, (int)(int16_t)(vb & 0xFFFFu), sb);
-                        float b1 = requant(s_pow43, (int)(int16_t)(vb >> 16), sb);
+                        float b0 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((((int)(vb << 16) >> 14) & 0x3FC) ^ 0x200)), sb);
+                        float b1 = __fmul_rn(*reinterpret_cast<const float*>(tab + (((((int)vb >> 16) << 2) & 0x3FC) ^ 0x200)), sb);
                         if (ms_now) {
                             const float l0 = __fadd_rn(a0, b0), r0 = __fsub_rn(a0, b0);
                             const float l1 = __fadd_rn(a1, b1), r1 = __fsub_rn(a1, b1);
@@ -449,6 +460,31 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                         *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(a0, b0, a1, b1);
                     } else {
                         *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(a0, a1);
+                    }
+                }
+                if (bigmask) {   // rare: |v| > 127 somewhere in this lane's coefficients
+#pragma unroll 1
+                    for (int m = 0; m < 9; m++) {
+                        if (!((bigmask >> m) & 1u)) continue;
+                        const int pi = lane + 32 * m;
+                        const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;
+                        const float sa = scf0[W.sfbpair[kind0][pi]];
+                        float a0 = requant(s_pow43, (int)(int16_t)(va & 0xFFFFu), sa);
+                        float a1 = requant(s_pow43, (int)(int16_t)(va >> 16), sa);
+                        if (NCH == 2) {
+                            const uint32_t vb = (pi >> 2) < nch1 ? isw1[pi] : 0u;
+                            const float sb = scf1[W.sfbpair[kind1][pi]];
+                            float b0 = requant(s_pow43, (int)(int16_t)(vb & 0xFFFFu), sb);
+                            float b1 = requant(s_pow43, (int)(int16_t)(vb >> 16), sb);
+                            if (ms_now) {
+                                const float l0 = __fadd_rn(a0, b0), r0 = __fsub_rn(a0, b0);
+                                const float l1 = __fadd_rn(a1, b1), r1 = __fsub_rn(a1, b1);
+                                a0 = l0; b0 = r0; a1 = l1; b1 = r1;
+                            }
+                            *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(a0, b0, a1, b1);
+                        } else {
+                            *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(a0, a1);
+                        }
                     }
                 }
             }
@@ -673,7 +709,12 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
 #ifndef L3B_EXP_SKIP_WINDOW
         if (act && mode == 2) {
             const uint64_t f0 = (uint64_t)g * 576u;   // first frame of this granule in the decoded signal
-            const bool inside = f0 >= skipf && f0 + 576u <= skipf + countf;
+            // samples [lo, hi) of this granule are delivered (all 576 except at the edges of the stream's PCM range)
+            const long long rel = (long long)skipf - (long long)f0;
+            const int dlo = (int)max(0ll, min(576ll, rel));
+            const int dhi = (int)max(0ll, min(576ll, rel + (long long)countf));
+            const unsigned span = (unsigned)(dhi - dlo);
+#define L3B_DELIVER(f) ((unsigned)((f) - dlo) < span)
             T* const out = pcm + (f0 - skipf);        // only dereferenced for delivered frames
             const float scale = 1.0f / 32768.0f;
             if (ii < 15) {
@@ -711,8 +752,8 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                         }
                         const int s = 2 * (3 * q3 + qq) + par;
                         const int fa = 32 * s + 15 - ii, fb = 32 * s + 17 + ii;
-                        if (inside || (f0 + fa >= skipf && f0 + fa - skipf < countf)) out[fa] = V::muls(a, scale);
-                        if (inside || (f0 + fb >= skipf && f0 + fb - skipf < countf)) out[fb] = V::muls(b, scale);
+                        if (L3B_DELIVER(fa)) out[fa] = V::muls(a, scale);
+                        if (L3B_DELIVER(fb)) out[fb] = V::muls(b, scale);
                     }
 #pragma unroll
                     for (int j = 0; j < 16; j++) Vw[j] = Vw[j + 6];   // slide by three slots
@@ -734,7 +775,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 a = V::add(a, V::muls(V::sub(z[8], z[6]), 37489.0f));
                 a = V::add(a, V::muls(z[7], 75038.0f));
                 const int fa = 32 * lane, fb = 32 * lane + 16;
-                if (inside || (f0 + fa >= skipf && f0 + fa - skipf < countf)) out[fa] = V::muls(a, scale);
+                if (L3B_DELIVER(fa)) out[fa] = V::muls(a, scale);
 #pragma unroll
                 for (int k = 0; k < 15; k += 2) z[k] = col[k * kDStride];
                 a = V::muls(z[14], 104.0f);
@@ -745,24 +786,46 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 a = V::add(a, V::muls(z[4], -45.0f));
                 a = V::add(a, V::muls(z[2], 146.0f));
                 a = V::add(a, V::muls(z[0], -5.0f));
-                if (inside || (f0 + fb >= skipf && f0 + fb - skipf < countf)) out[fb] = V::muls(a, scale);
+                if (L3B_DELIVER(fb)) out[fb] = V::muls(a, scale);
             }
         }
 #endif
+#undef L3B_DELIVER
         // slide the history: the last 15 slots become rows 0..14 (qmf_state, minimp3.d:1423-1433)
         if (act && mode >= 1) {
             __syncwarp();
-            T tmp[16];
+            if (NCH == 2) {
+                // 15 x 33 float2 = 495 elements moved down by 18 rows.  D is 8 bytes past a 16-byte boundary, and so is
+                // D + 18 rows: element 0 goes alone, elements 1..494 as 247 16-byte vectors.
+                const float4* src = reinterpret_cast<const float4*>(D + 18 * kDStride + 1);
+                float4* dst = reinterpret_cast<float4*>(D + 1);
+                const T first = D[18 * kDStride];
+                float4 tmp[8];
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const int e = lane + 32 * m;
-                if (e < 15 * kDStride) tmp[m] = D[18 * kDStride + e];
-            }
-            __syncwarp();
+                for (int m = 0; m < 8; m++) {
+                    const int e = lane + 32 * m;
+                    if (e < 247) tmp[m] = src[e];
+                }
+                __syncwarp();
+                if (lane == 0) D[0] = first;
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const int e = lane + 32 * m;
-                if (e < 15 * kDStride) D[e] = tmp[m];
+                for (int m = 0; m < 8; m++) {
+                    const int e = lane + 32 * m;
+                    if (e < 247) dst[e] = tmp[m];
+                }
+            } else {
+                T tmp[16];
+#pragma unroll
+                for (int m = 0; m < 16; m++) {
+                    const int e = lane + 32 * m;
+                    if (e < 15 * kDStride) tmp[m] = D[18 * kDStride + e];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < 16; m++) {
+                    const int e = lane + 32 * m;
+                    if (e < 15 * kDStride) D[e] = tmp[m];
+                }
             }
             __syncwarp();
         }
@@ -773,7 +836,8 @@ template <int NCH, int WARPS>
 static void launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n, cudaStream_t s) {
     if (!n) return;
     static bool configured = false;
-    const size_t smem = 1040 + (size_t)WARPS * sizeof(WarpSmem<NCH>);
+    static const size_t pad = getenv("L3B_GRANULE_SMEM_PAD") ? (size_t)atoi(getenv("L3B_GRANULE_SMEM_PAD")) : 0;   // occupancy experiments
+    const size_t smem = 1040 + (size_t)WARPS * sizeof(WarpSmem<NCH>) + pad;
     if (!configured) {
         cudaFuncSetAttribute(l3_granule_kernel<NCH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;

@@ -8,7 +8,8 @@ A "step" is one pass of the hot path over one batch of synthetic streams.  At N=
 BASELINE.json configs[1]: 1,024 synthetic 60 s 44.1 kHz stereo 128 kbps MPEG-1 Layer III long-block
 streams (seeds 0..1023).  N>1: streams shard by file, 1,024 streams per GPU, no collective (weak scaling).
 
-`value`   device-resident throughput: bitstreams + descriptors already in HBM, entropy + granule kernels.
+`value`   device-resident throughput: bitstreams + descriptors already in HBM; one step = scalefactor kernel +
+          big_values kernel + count1 kernel (integer, "entropy") + fused granule kernel (float).
 `e2e`     MP3 bytes in host memory -> float PCM in pinned host memory through the public batch API:
           host prepass (frame sync / side info / reservoir slicing, all host threads) + H2D + kernels + D2H.
 `roofline` of the dominant (granule) kernel; `cpu_baseline`: the C oracle (port of the D reference, which
@@ -35,6 +36,9 @@ METRIC = "mp3_batch_decode_audio_seconds_per_second"
 UNIT = "audio-s/s"
 FLOPS_PER_GRCH = 32734          # SURVEY.md 8d / BASELINE.md 3: float add/sub/mul per granule-channel
 FP32_NOMINAL_TFLOPS = 74.45     # 148 SM x 128 lanes x 2 x 1.965 GHz (not measured by the driver)
+# tools/microbench/fp32_pipes.cu on this pool's B200: FMUL / FADD / FADD2 / FMUL2 all retire ~125 lane-ops per clock per SM
+# (3.8 scalar or 1.95 packed warp-instructions): the FP32 pipe does 148 x 125 x 1.965e9 = 36.4e12 un-fused flop/s
+FP32_UNFUSED_MEASURED_TFLOPS = 36.4
 HBM_FALLBACK_GBS = 6650.0       # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -301,22 +305,26 @@ def main():
     # DRAM traffic of the same kernel on the same workload, from one `ncu --set full` capture (profiles/r01_traffic.json);
     # only quoted when this run IS that workload
     traffic = None
-    tf = ROOT / "profiles" / "r01_traffic.json"
+    tf = ROOT / "profiles" / "r01b_traffic.json"
     if tf.exists() and args.streams == 1024 and args.seconds == 60.0:
         traffic = json.loads(tf.read_text()).get("granule", {}).get("traffic")
     roofline = {"bound": "hbm", "kernel": "l3_granule_kernel<2,4>", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak, "peak_source": "measured" if peaks else "fallback", "traffic": traffic,
                 "traffic_note": "ncu dram read+write per launch; above the algorithmic bytes because the kernel reads the int16 "
-                                "spectra written by the entropy kernel (10.8 GB) and PCM sectors are written in two passes",
+                                "spectra and the 256-byte scalefactor/gain records written by the entropy kernels",
                 "ms_per_launch": gran_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "fp32": {"achieved_tflops": fp32_tflops, "peak_tflops_nominal": FP32_NOMINAL_TFLOPS,
                          "frac": fp32_tflops / FP32_NOMINAL_TFLOPS,
+                         "unfused_pipe_peak_tflops_measured": FP32_UNFUSED_MEASURED_TFLOPS,
+                         "frac_of_unfused_pipe_peak": fp32_tflops / FP32_UNFUSED_MEASURED_TFLOPS,
                          "note": "flops counted un-fused (32,734 per granule-channel); the kernel is compiled -fmad=false for "
-                                 "bit-exactness, so 0.5 is its ceiling against the FMA-counted nominal peak"},
+                                 "bit-exactness, so every flop takes one FP32-pipe lane slot: the measured un-fused pipe peak "
+                                 "(tools/microbench/fp32_pipes.cu) is its real ceiling, half the FMA-counted nominal one"},
                 "slower_roof": "fp32" if fp32_ceiling < hbm_ceiling else "hbm",
                 "frac_of_slower_roof_whole_step": (audio_s / (step_ms * 1e-3)) / min(fp32_ceiling, hbm_ceiling) if world == 1 else None,
-                "entropy_kernel_ms": ent_ms, "granule_kernel_share_of_step": min(1.0, gran_ms / (kern_ms[2] / nk)),
-                "kernels_overlap": "entropy launches (stream A) and granule launches (stream B) of different sub-batches run concurrently"}
+                "entropy_kernels_ms": ent_ms, "granule_kernel_share_of_step": min(1.0, gran_ms / (kern_ms[2] / nk)),
+                "kernels": ["l3_scf_kernel", "l3_huff_big_kernel<8,8>", "l3_huff_c1_kernel<8>", "l3_granule_kernel<2,4>"],
+                "kernels_note": "one launch of each per step, in that order; entropy_kernels_ms spans the first three"}
 
     # ---- end to end: MP3 bytes (host) -> PCM floats (pinned host) ------------------------------------------
     # Through the public batch API (audio_formats_b200.BatchPipeline): per wave host prepass (frame sync, side
