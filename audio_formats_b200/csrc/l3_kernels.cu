@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             __syncwarp();
             // the staging buffers are free again: fetch the next granule while this one is transformed
             if (lane == 0 && it + 1 < n_iter) {
-                fence_proxy_async();
+                fence_proxy_async();   // measured free (19.64 ms with or without); kept for the generic -> async proxy ordering
                 prefetch(g + 1);
             }
 

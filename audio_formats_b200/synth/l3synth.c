@@ -87,7 +87,8 @@ static int resolve_format(const l3s_params_t* p, fmt_t* f)
     f->br_idx = 0;
     for (int i = 1; i < 15; i++)
         if (rates[i] == p->bitrate_kbps) f->br_idx = i;
-    if (!f->br_idx) return -1;
+    if (!f->br_idx && !p->free_format) return -1;
+    if (p->free_format) f->br_idx = 0;   /* bitrate index 0: the decoder finds the frame size by searching for the next header */
     if (p->nch != 1 && p->nch != 2) return -1;
     f->side_bytes = f->mpeg1 ? (p->nch == 1 ? 17 : 32) : (p->nch == 1 ? 9 : 17);
     f->ngr = f->mpeg1 ? 2 : 1;

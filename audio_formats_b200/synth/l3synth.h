@@ -29,6 +29,7 @@ typedef struct {
     int id3v1;         /* 1: append a 128-byte ID3v1 tag */
     int emphasis_bits; /* low 4 bits of header byte 3 (copyright/original/emphasis) */
     int mixed_only_short; /* 1: mixed_block_flag only on the short blocks of a mixed run, not on its start/stop blocks */
+    int free_format;   /* 1: write bitrate index 0 (free format); bitrate_kbps may then be any value (frame <= 2304 bytes) */
 } l3s_params_t;
 
 typedef struct {

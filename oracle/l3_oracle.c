@@ -1031,6 +1031,7 @@ int l3o_decode_frame(l3o_dec_t* dec, const uint8_t* mp3, int mp3_bytes, float* p
     const uint8_t* hdr;
     bitrd_t bs_frame[1];
     scratch_t scratch;
+    memset(&scratch, 0, sizeof scratch); /* D default-initialises locals (minimp3.d:1497): bytes and ints start at 0 */
 
     if (mp3_bytes > 4 && dec->header[0] == 0xff && hdr_compare(dec->header, mp3)) {
         frame_size = l3o_hdr_frame_bytes(mp3, dec->free_format_bytes) + l3o_hdr_padding(mp3);

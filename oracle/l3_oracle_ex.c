@@ -98,7 +98,7 @@ int l3o_detect_cb(l3o_io_t* io, uint8_t* buf, size_t buf_size)
         skip_id3v1(buf, &filled);
         if (filled > BUF_SIZE) filled = BUF_SIZE;
     }
-    int free_format_bytes, frame_size;
+    int free_format_bytes = 0, frame_size = 0; /* D default-initialises locals (int.init == 0): minimp3_ex.d:228 relies on it */
     l3o__find_frame(buf, (int)filled, &free_format_bytes, &frame_size);
     if (frame_size) return 0; /* MAX_FRAME_SYNC_MATCHES consecutive frames found */
     return L3O_E_USER;

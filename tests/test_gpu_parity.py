@@ -72,6 +72,16 @@ def test_mixed_block_flag_on_start_and_stop_blocks(ctx, hz, rate, only_short):
         check_stream(ctx, synth.generate(p, want_quantised=True), f"mixed flag {hz} {nch}ch only_short={only_short}")
 
 
+@pytest.mark.parametrize("hz,nch,kbps,nopad", [(44100, 2, 150, 1), (48000, 1, 100, 0), (22050, 2, 70, 0), (32000, 2, 500, 1)])
+def test_free_format(ctx, hz, nch, kbps, nopad):
+    """Free-format streams (bitrate index 0, frame size found by header search, up to 2,304-byte frames)."""
+    from audio_formats_b200 import synth
+    p = synth.SynthParams(seed=70 + nch, hz=hz, nch=nch, bitrate_kbps=kbps, nframes=60, free_format=1, no_padding=nopad,
+                          block_mode=1 if hz >= 32000 else 2, stereo_mode=2 if nch == 2 else 0, reservoir=2, scfsi=1,
+                          small_scalefactors=0)
+    check_stream(ctx, synth.generate(p, want_quantised=True), f"free format {hz} {nch}ch {kbps} kbps")
+
+
 def test_config5_320kbps(ctx):
     from audio_formats_b200 import synth
     check_stream(ctx, synth.generate(synth.config5_params(5, 6.0), want_quantised=True), "config5")

@@ -37,6 +37,21 @@ def test_clean_streams(built, cfg):
     assert (np.diff(d["bit_start"].reshape(-1).astype(np.int64)) >= 0).all()   # bit offsets grow monotonically
 
 
+@pytest.mark.parametrize("hz,nch,kbps,nopad", [(44100, 2, 150, 1), (48000, 1, 100, 0), (22050, 2, 70, 0), (44100, 2, 400, 0),
+                                                (32000, 2, 500, 1), (11025, 1, 20, 0)])
+def test_free_format(built, hz, nch, kbps, nopad):
+    """Bitrate index 0: the frame size comes from searching for the next matching header (minimp3.d:1460-1472,
+    hdr_frame_bytes :270-278).  The index pass counts two frames fewer than the read loop decodes (it needs two
+    following headers); the prepass has to reproduce both numbers."""
+    from audio_formats_b200 import synth
+    p = synth.SynthParams(seed=60 + nch, hz=hz, nch=nch, bitrate_kbps=kbps, nframes=40, free_format=1, no_padding=nopad,
+                          block_mode=1 if hz >= 32000 else 2, stereo_mode=1 if nch == 2 else 0, reservoir=2)
+    st = synth.generate(p)
+    sc, pcm, taps = scan_vs_oracle(st.data, f"free format {hz} {nch} {kbps}")
+    assert sc.granules == len(taps) == st.granules
+    assert pcm.shape[0] == st.frames * st.samples_per_frame
+
+
 def test_tags_and_crc(built):
     from audio_formats_b200 import synth
     p = replace(synth.config3_params(12, 2.0), crc=1, id3v2_bytes=4096, id3v1=1)
