@@ -5,11 +5,13 @@
 // granule-channels runs as long as its slowest lane: on the 128 kbps bench streams that wastes half of all lane
 // slots.  Here the lanes of a warp are decoupled instead:
 //
-//   l3_scf_kernel       one thread per granule-channel: scalefactors (minimp3.d:613-644, 659-712) -> scalefactor
-//                       record; and a 32-byte HuffJob (bit window, region books, limits) for the two kernels below
+//   l3_scf_kernel       one thread per granule-channel: scalefactors (minimp3.d:613-644, 659-712) and band gains
+//                       (minimp3.d:714-719) -> 256-byte record; and a 48-byte HuffJob (bit position and window,
+//                       region books, limits) for the two kernels below
 //   l3_huff_big_kernel  persistent warps; every LANE pulls granule-channels from a global counter and decodes their
 //                       big_values pairs (minimp3.d:789-853), four pairs (one 16-byte chunk) per trip; a lane that
-//                       runs out of pairs parks until enough lanes are free, then they refill together
+//                       runs out of pairs parks until enough lanes are free, then they write their hand-over to
+//                       count1 and refill together; bit-stream words arrive through a cp.async ring
 //   l3_huff_c1_kernel   same scheme for the count1 quads (minimp3.d:855-882), continuing at the bit position the
 //                       big_values kernel left in the job
 //
@@ -402,8 +404,18 @@ __global__ void __launch_bounds__(32 * WARPS) l3_huff_big_kernel(BatchParams p, 
     bw.ring = smem_addr(s_after_lut + WARPS * 96 * 4 + warp * (kRingWords * 32) + lane);
     uint32_t item = 0, widx = 0, bvw = 0, nbw = 0, r2w = 0, par1 = 0, par2 = 0;
     uint32_t cur_base = lut, cur_sh = 31, cur_lin = 0;   // current region's book: LUT address, 32 - root bits, linbits
-    bool have = false;
+    bool have = false, parked = false;   // parked: finished its pairs, hand-over to count1 not written yet
+    uint32_t last[4] = {0, 0, 0, 0};      // the last output chunk of a parked lane
     const uint4* const jobs_u4 = reinterpret_cast<const uint4*>(jobs);
+    // What count1 needs, written into the job in place of what big_values no longer needs.  Done when the lane
+    // refills (several lanes at once) instead of in the trip the lane finished in (one lane at a time).
+    auto hand_over = [&]() {
+        uint4* jw = reinterpret_cast<uint4*>(jobs + item);
+        reinterpret_cast<uint32_t*>(jw)[2] = bw.pos;
+        jw[1] = make_uint4(last[0], last[1], last[2], last[3]);   // the chunk count1 continues in (only used when bvw & 3)
+        jw[2] = bw.close();
+        parked = false;
+    };
     JobPool<false> jp;
     jp.init(reinterpret_cast<uint4*>(s_after_lut) + warp * 96, counter, jobs_u4, nullptr, n_items, lane);
 
@@ -411,6 +423,7 @@ __global__ void __launch_bounds__(32 * WARPS) l3_huff_big_kernel(BatchParams p, 
         const unsigned need = __ballot_sync(0xffffffffu, !have);
         if (__popc(need) >= K && !jp.empty()) {
             cp_async_wait_all();   // nothing of a finished job may still be landing in a ring that is about to be re-primed
+            if (parked) hand_over();
             const int slot = jp.draw(need, !have, lane);
             if (slot >= 0) {
                 const uint4 a = jp.pool[3 * slot], b = jp.pool[3 * slot + 1], w = jp.pool[3 * slot + 2];
@@ -481,15 +494,14 @@ __global__ void __launch_bounds__(32 * WARPS) l3_huff_big_kernel(BatchParams p, 
         }
         if (act) {
             is_base[(uint64_t)item * kIsChunks + chunk] = make_uint4(q[0], q[1], q[2], q[3]);
-            if (widx >= bvw) {
-                uint4* jw = reinterpret_cast<uint4*>(jobs + item);
-                reinterpret_cast<uint32_t*>(jw)[2] = bw.pos;
-                jw[1] = make_uint4(q[0], q[1], q[2], q[3]);   // the chunk count1 continues in (only used when bvw & 3)
-                jw[2] = bw.close();
+            if (widx >= bvw) {   // through: park; the hand-over to count1 is written when the lane refills
                 have = false;
+                parked = true;
+                last[0] = q[0]; last[1] = q[1]; last[2] = q[2]; last[3] = q[3];
             }
         }
     }
+    if (parked) hand_over();
     cp_async_wait_all();
 }
 
@@ -520,7 +532,7 @@ __global__ void __launch_bounds__(128) l3_huff_c1_kernel(BatchParams p, uint32_t
     bw.words = blob32; bw.nwords = 1; bw.pos = 0; bw.w0 = bw.w1 = 0; bw.wn = bw.ready = bw.filled = 0;
     bw.ring = smem_addr(&s_words[warp][0][lane]);
     uint32_t item = 0, widx = 0, limit = 0, cbase = 0;
-    bool have = false, fin = false;
+    bool have = false, fin = false, parked = false;
     const uint4* const jobs_u4 = reinterpret_cast<const uint4*>(jobs);
     JobPool<true> jp;
     jp.init(&s_pool[warp][0], counter, jobs_u4, descs, n_items, lane);
@@ -529,11 +541,25 @@ __global__ void __launch_bounds__(128) l3_huff_c1_kernel(BatchParams p, uint32_t
         const uint32_t* r = ring + (chunk & 1u) * 128u;
         is_base[(uint64_t)item * kIsChunks + chunk] = make_uint4(r[0], r[32], r[64], r[96]);
     };
+    // tail of a finished granule-channel: pad and write the last chunk, record the number of chunks.  Done when the
+    // lane refills (several lanes at once) instead of in the trip it finished in.
+    auto finish = [&]() {
+        if (widx & 3u) {   // pad the last chunk with zeros
+            for (uint32_t k = widx & 3u; k < 4; k++) ring[((widx & 4u) + k) * 32u] = 0u;
+            flush(widx >> 2);
+        }
+        const uint32_t chunks = (widx + 3u) >> 2;
+        *reinterpret_cast<uint16_t*>(sf_base + (uint64_t)item * kSfRecBytes + 80) = (uint16_t)chunks;
+        if (p.zero_fill)
+            for (uint32_t c = chunks; c < (uint32_t)kIsChunks; c++) is_base[(uint64_t)item * kIsChunks + c] = make_uint4(0, 0, 0, 0);
+        parked = false;
+    };
 
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, !have);
         if (__popc(need) >= K && !jp.empty()) {
             cp_async_wait_all();   // nothing of a finished job may still be landing in a ring that is about to be re-primed
+            if (parked) finish();
             const int slot = jp.draw(need, !have, lane);
             if (slot >= 0) {
                 const uint4 a = jp.pool[3 * slot], part = jp.pool[3 * slot + 1], w = jp.pool[3 * slot + 2];
@@ -582,18 +608,9 @@ __global__ void __launch_bounds__(128) l3_huff_c1_kernel(BatchParams p, uint32_t
                 }
             }
         }
-        if (have && fin) {   // once per trip for all the lanes that ended in it
-            if (widx & 3u) {   // pad the last chunk with zeros
-                for (uint32_t k = widx & 3u; k < 4; k++) ring[((widx & 4u) + k) * 32u] = 0u;
-                flush(widx >> 2);
-            }
-            const uint32_t chunks = (widx + 3u) >> 2;
-            *reinterpret_cast<uint16_t*>(sf_base + (uint64_t)item * kSfRecBytes + 80) = (uint16_t)chunks;
-            if (p.zero_fill)
-                for (uint32_t c = chunks; c < (uint32_t)kIsChunks; c++) is_base[(uint64_t)item * kIsChunks + c] = make_uint4(0, 0, 0, 0);
-            have = false;
-        }
+        if (have && fin) { have = false; parked = true; }   // finished: the tail is written when the lane refills
     }
+    if (parked) finish();
     cp_async_wait_all();
 }
 
