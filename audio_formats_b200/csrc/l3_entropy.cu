@@ -155,16 +155,24 @@ __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
         part += k + 4;  // the reference's for-loop increments k once more before its exit test (minimp3.d:683-691)
         scfsi = -16;
     }
-    // granule-0 scalefactors for scfsi copies (MPEG-1 granule 1 only; both granules are long blocks then)
+    // scfsi copies (MPEG-1 only).  The reference copies from `ist_pos`, per-frame scratch that starts zeroed (D default
+    // initialisation, minimp3.d:1497) and holds granule 0's values when granule 1 is read (minimp3.d:619-622):
+    //  * granule 1 copies what granule 0 of the same channel READ (both are long-type blocks then: a short block
+    //    clears the bits, minimp3.d:568); the values are fetched again from granule 0's bit field;
+    //  * granule 0 can have scfsi bits too -- the private bits leak into them (minimp3.d:530-540, 600-601) -- and
+    //    then "copies" zeros and does not read that partition; granule 1 in turn copies those zeros.
     uint32_t g0_slen = 0, g0_bits = 0;
+    int g0_nib = 0;              // granule 0's own scfsi nibble (partitions it did not read)
+    bool from_zero = false;      // this IS granule 0: the copy source is the zeroed scratch
     if (scfsi > 0 && d.second_granule() && gi >= S->first_grch + (uint64_t)nch) {
         const Desc d0 = load_desc(p.grch + gi - nch);
         const int pp = e_scfc_decode[d0.scalefac_compress() & 15];
         const uint32_t a = (uint32_t)(pp >> 2), b = (uint32_t)(pp & 3);
         g0_slen = a | (a << 8) | (b << 16) | (b << 24);
         g0_bits = d0.bit_start;
+        g0_nib = d0.scfsi();
     } else if (scfsi > 0) {
-        scfsi = 0;  // no granule 0 to copy from
+        from_zero = true;
     }
     {
         const int sbg_sh = 3 - scf_shift;
@@ -176,10 +184,11 @@ __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
             const int bits = (slen >> (8 * i)) & 0xFF;
             const int bits0 = (g0_slen >> (8 * i)) & 0xFF;
             const bool copy = (scfsi & 8) != 0;
+            const bool src_zero = from_zero || (g0_nib & 8) || !bits0;   // the source partition was never read: zeros
             for (int k = 0; k < cnt; k++, n++) {
                 int s, ip;
                 if (copy) {
-                    s = bits0 ? (int)br.peek_at(g0_off + (uint32_t)(k * bits0), bits0) : 0;
+                    s = src_zero ? 0 : (int)br.peek_at(g0_off + (uint32_t)(k * bits0), bits0);
                     ip = s;
                 } else if (!bits) {
                     s = 0; ip = 0;
@@ -193,8 +202,9 @@ __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
                 rec[n] = (uint8_t)(s + adj);
                 rec[40 + n] = (uint8_t)ip;
             }
-            g0_off += (uint32_t)(cnt * bits0);
+            if (!(g0_nib & 8)) g0_off += (uint32_t)(cnt * bits0);   // granule 0 skipped the partitions it "copied"
             scfsi *= 2;
+            g0_nib *= 2;
         }
         for (int j = 0; j < 3 && n < 40; j++, n++) {  // scf[0] = scf[1] = scf[2] = 0 after the last partition
             int adj = 0;

@@ -217,7 +217,8 @@ static int next_block_type(const l3s_params_t* p, chan_state_t* cs, rng_t* r, in
 /* Fill one granule-channel within `budget` bits. `force_zero_above` (>=0): coefficients at or above
  * that index must stay zero (used to give intensity stereo something to do on channel 1). */
 static void plan_grch(const l3s_params_t* p, const fmt_t* f, rng_t* r, grch_t* g, int budget, int block_type, int mixed,
-                      int gr_index, int ch, int istereo_ch1, int allow_scfsi, const grch_t* gr0, int force_zero_above)
+                      int gr_index, int ch, int istereo_ch1, int allow_scfsi, const grch_t* gr0, int force_zero_above,
+                      int leaked_nibble)
 {
     memset(g, 0, sizeof *g);
     if (budget > 4095) budget = 4095;
@@ -246,6 +247,10 @@ static void plan_grch(const l3s_params_t* p, const fmt_t* f, rng_t* r, grch_t* g
         slen[2] = slen[3] = (uint8_t)(pp & 3);
         g->scalefac_compress = sfc;
         g->scfsi = 0;
+        /* granule 0: the reference reads the private bits together with scfsi and they end up as THIS granule-channel's
+         * scfsi nibble (minimp3.d:530-540, 600-601); a flagged partition is then "copied" from the frame's zeroed scratch
+         * and its bits are not read -- so they must not be written either.  Short blocks clear the nibble (:568). */
+        if (gr_index == 0 && block_type != 2) g->scfsi = leaked_nibble;
         if (allow_scfsi && gr_index == 1 && block_type != 2 && gr0 && gr0->block_type != 2 && rng_chance(r, 1, 2))
             g->scfsi = (int)rng_below(r, 16);
     } else {
@@ -410,15 +415,15 @@ static void emit_grch(bitwr_t* w, const grch_t* g, const fmt_t* f)
 }
 
 /* ---------------------------------------------------------------- side info + header */
-static void write_side_info(bitwr_t* w, const fmt_t* f, int nch, int mdb, const grch_t* g /* [ngr][nch] */)
+static void write_side_info(bitwr_t* w, const fmt_t* f, int nch, int mdb, const grch_t* g /* [ngr][nch] */, int private_bits)
 {
     if (f->mpeg1) {
         bw_put(w, (uint32_t)mdb, 9);
-        bw_put(w, 0, nch == 1 ? 5 : 3); /* private bits = 0 (they leak into scfsi, SURVEY 8c quirk i) */
+        bw_put(w, (uint32_t)private_bits, nch == 1 ? 5 : 3); /* they leak into granule 0's scfsi in the reference (SURVEY 8c quirk i) */
         for (int ch = 0; ch < nch; ch++) bw_put(w, (uint32_t)g[1 * nch + ch].scfsi, 4);
     } else {
         bw_put(w, (uint32_t)mdb, 8);
-        bw_put(w, 0, nch == 1 ? 1 : 2);
+        bw_put(w, (uint32_t)private_bits & (nch == 1 ? 1u : 3u), nch == 1 ? 1 : 2); /* read and dropped by the reference (minimp3.d:534) */
     }
     for (int gr = 0; gr < f->ngr; gr++)
         for (int ch = 0; ch < nch; ch++) {
@@ -487,6 +492,7 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
     int* mdb_of = (int*)malloc(nfr * sizeof(int));
     grch_t* plans = (grch_t*)malloc(nfr * (size_t)(ngr * nch) * sizeof(grch_t));
     uint8_t* hdr3 = (uint8_t*)malloc(nfr);
+    uint8_t* priv = (uint8_t*)calloc(nfr, 1);
 
     size_t slot_start = 0;
     long long granules_out = 0;
@@ -513,6 +519,7 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
             }
         }
         hdr3[fi] = (uint8_t)((mode << 6) | (mode_ext << 4) | (p->emphasis_bits & 0xF));
+        if (p->private_bits) priv[fi] = (uint8_t)rng_below(&rng, nch == 1 ? 32 : 8);
 
         /* how much of what is available this frame uses */
         double use;
@@ -552,8 +559,11 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
                 int budget = (int)(share * (0.6 + 0.8 * rng_unit(&rng)));
                 if (budget > left) budget = left;
                 if (remaining_parts == 1) budget = left;
+                /* MPEG-1: stereo -> the three private bits become granule 0 / channel 1's scfsi nibble; mono -> the first of
+                 * the five private bits becomes granule 0's lowest scfsi bit */
+                const int leaked = !f.mpeg1 ? 0 : (nch == 2 ? (ch == 1 ? priv[fi] & 7 : 0) : (priv[fi] >> 4) & 1);
                 plan_grch(p, &f, &rng, &G[k], budget, bt[ch], mx[ch], gr, ch, (mode_ext & 1) && ch == 1, p->scfsi,
-                          gr == 1 ? &G[ch] : NULL, zero_above[ch]);
+                          gr == 1 ? &G[ch] : NULL, zero_above[ch], leaked);
                 left -= G[k].part23;
                 emit_grch(&mw, &G[k], &f);
                 if (is_out) memcpy(is_out + (granules_out * nch + ch) * 576, G[k].is, 576 * sizeof(int16_t));
@@ -562,7 +572,7 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
         }
         slot_start += (size_t)slot[fi];
         if (((mw.pos + 7) >> 3) > slot_start) { /* internal error: overran the slot */
-            free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3);
+            free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3); free(priv);
             return -2;
         }
     }
@@ -571,7 +581,7 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
     size_t o = 0;
     size_t need = (size_t)p->id3v2_bytes + (p->id3v1 ? 128 : 0);
     for (size_t i = 0; i < nfr; i++) need += (size_t)fbytes[i];
-    if (need > cap) { free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3); return -3; }
+    if (need > cap) { free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3); free(priv); return -3; }
     memset(out, 0, need);
     if (p->id3v2_bytes >= 10) {
         int body = p->id3v2_bytes - 10;
@@ -591,7 +601,7 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
         size_t q = 4;
         if (p->crc) { h[4] = 0xAB; h[5] = 0xCD; q = 6; } /* never verified by the reference (minimp3.d:1533-1536) */
         bitwr_t sw = {h + q, (size_t)f.side_bytes, 0, 0};
-        write_side_info(&sw, &f, nch, mdb_of[fi], plans + fi * (size_t)(ngr * nch));
+        write_side_info(&sw, &f, nch, mdb_of[fi], plans + fi * (size_t)(ngr * nch), priv[fi]);
         memcpy(h + q + f.side_bytes, md + sp, (size_t)slot[fi]);
         sp += (size_t)slot[fi];
         o += (size_t)fbytes[fi];
@@ -608,6 +618,6 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
         info_out->mpeg1 = f.mpeg1;
         info_out->sr_idx = f.sr_idx;
     }
-    free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3);
+    free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3); free(priv);
     return (long long)o;
 }

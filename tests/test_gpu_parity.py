@@ -82,6 +82,18 @@ def test_free_format(ctx, hz, nch, kbps, nopad):
     check_stream(ctx, synth.generate(p, want_quantised=True), f"free format {hz} {nch}ch {kbps} kbps")
 
 
+@pytest.mark.parametrize("hz,nch,rate", [(44100, 2, 128), (48000, 1, 96), (32000, 2, 160), (22050, 2, 64), (16000, 1, 32)])
+def test_private_bits_leak_into_scfsi(ctx, hz, nch, rate):
+    """The reference reads the private bits together with scfsi, so in MPEG-1 they act as granule 0's scfsi nibble
+    (minimp3.d:530-540, 600-601): a flagged partition is copied from the frame's zeroed scratch and its bits are not
+    read.  Files with private bits set decode that way in the reference, so they must here (MPEG-2 drops the bits)."""
+    from audio_formats_b200 import synth
+    p = synth.SynthParams(seed=500 + hz // 100 + nch, hz=hz, nch=nch, bitrate_kbps=rate, nframes=120, private_bits=1, scfsi=1,
+                          block_mode=1 if hz >= 32000 else 2, stereo_mode=2 if nch == 2 else 0, reservoir=2,
+                          small_scalefactors=0)
+    check_stream(ctx, synth.generate(p, want_quantised=True), f"private bits {hz} {nch}ch")
+
+
 def test_config5_320kbps(ctx):
     from audio_formats_b200 import synth
     check_stream(ctx, synth.generate(synth.config5_params(5, 6.0), want_quantised=True), "config5")
@@ -191,5 +203,5 @@ def test_random_generator_profiles(ctx, seed):
                           small_scalefactors=int(rng.integers(0, 2)), table_cycle=int(rng.integers(0, 2)),
                           table_cycle_pos=seed, no_padding=int(rng.integers(0, 2)),
                           id3v2_bytes=int(rng.choice([0, 0, 10, 777])), id3v1=int(rng.integers(0, 2)),
-                          mixed_only_short=int(seed % 3 == 0))
+                          mixed_only_short=int(seed % 3 == 0), private_bits=int(seed % 4 == 1))
     check_stream(ctx, synth.generate(p, want_quantised=True), f"random[{seed}] {p}")

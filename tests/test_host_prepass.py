@@ -52,6 +52,18 @@ def test_free_format(built, hz, nch, kbps, nopad):
     assert pcm.shape[0] == st.frames * st.samples_per_frame
 
 
+@pytest.mark.parametrize("nch", [1, 2])
+def test_private_bits(built, nch):
+    """Private bits set (they become granule 0's scfsi nibble in the reference): same frames, same lengths."""
+    from audio_formats_b200 import synth
+    p = synth.SynthParams(seed=80 + nch, nch=nch, bitrate_kbps=128 // (3 - nch), nframes=50, private_bits=1, scfsi=1, block_mode=1)
+    st = synth.generate(p)
+    sc, pcm, taps = scan_vs_oracle(st.data, f"private bits {nch}ch")
+    assert sc.granules == len(taps) == st.granules
+    d = sc.descs.reshape(sc.granules, nch)
+    assert ((d["w2"][0::2] >> 27) & 15).any()        # some granule 0 carries a leaked nibble
+
+
 def test_tags_and_crc(built):
     from audio_formats_b200 import synth
     p = replace(synth.config3_params(12, 2.0), crc=1, id3v2_bytes=4096, id3v1=1)
