@@ -562,6 +562,19 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 }
                 __syncwarp();
             }
+            // A MONO frame whose header has the intensity bit set (mode_extension is "don't care" outside joint stereo,
+            // but HDR_TEST_I_STEREO looks at the bit in every mode, minimp3.d:100, 1207): the reference runs
+            // L3_intensity_stereo on (this channel, a zeroed second channel, zeroed ist_pos): every band is "intensity"
+            // with position 0, so the spectrum is multiplied by kl*s -- g_pan[0] = 0 in MPEG-1 (the frame goes silent,
+            // signed zeros included), 1 in MPEG-2 -- with s = sqrt(2) when the MS bit is set too (minimp3.d:928-961).
+            if (NCH == 1 && (hb & 1)) {
+                const float s = (hb & 2) ? 1.41421356f : 1.0f;
+                const float k = __fmul_rn(mpeg1 ? c_pan[0] : 1.0f, s);
+                float* X = reinterpret_cast<float*>(xr);
+#pragma unroll 6
+                for (int m = 0; m < 18; m++) X[lane + 32 * m] = __fmul_rn(X[lane + 32 * m], k);
+                __syncwarp();
+            }
         }
         L3B_PHASE_SYNC();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
 

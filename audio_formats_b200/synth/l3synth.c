@@ -454,7 +454,8 @@ size_t l3s_max_bytes(const l3s_params_t* p)
 {
     fmt_t f;
     if (resolve_format(p, &f)) return 0;
-    size_t per = (size_t)((f.mpeg1 ? 144000 : 72000) * p->bitrate_kbps / p->hz) + 2;
+    const int top = p->vbr ? (f.mpeg1 ? 320 : 160) : p->bitrate_kbps;
+    size_t per = (size_t)((f.mpeg1 ? 144000 : 72000) * top / p->hz) + 2;
     return per * (size_t)p->nframes + 8192 + (size_t)p->id3v2_bytes + (p->id3v1 ? 128 : 0);
 }
 
@@ -473,6 +474,9 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
     size_t nfr = (size_t)p->nframes;
     int* fbytes = (int*)malloc(nfr * sizeof(int));
     int* slot = (int*)malloc(nfr * sizeof(int));
+    uint8_t* bri = (uint8_t*)malloc(nfr);   /* bitrate index and padding bit of every frame */
+    uint8_t* padb = (uint8_t*)malloc(nfr);
+    rng_t vrng = {p->seed * 0x9E3779B97F4A7C15ull + 0x7654321};   /* its own stream: vbr = 0 streams are unchanged */
     long long rem = 0;
     size_t total_slots = 0;
     for (size_t i = 0; i < nfr; i++) {
@@ -481,9 +485,18 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
         int pad = 0;
         if (rem >= p->hz) { rem -= p->hz; pad = 1; }
         if (p->no_padding) pad = 0;
+        bri[i] = (uint8_t)f.br_idx;
+        if (p->vbr && !p->free_format) {   /* the bitrate index (and padding bit) may change from frame to frame (minimp3.d:241-247) */
+            const int* rates = f.mpeg1 ? k_rates_m1 : k_rates_m2;
+            int lo = f.br_idx - 4 < 1 ? 1 : f.br_idx - 4, hi = f.br_idx + 3 > 14 ? 14 : f.br_idx + 3;
+            bri[i] = (uint8_t)(lo + (int)rng_below(&vrng, (uint32_t)(hi - lo + 1)));
+            base = (int)((long long)spf / 8 * rates[bri[i]] * 1000 / p->hz);
+            pad = p->no_padding ? 0 : (int)rng_below(&vrng, 2);
+        }
+        padb[i] = (uint8_t)pad;
         fbytes[i] = base + pad;
         slot[i] = fbytes[i] - 4 - (p->crc ? 2 : 0) - f.side_bytes;
-        if (slot[i] < 0) { free(fbytes); free(slot); return -1; }
+        if (slot[i] < 0) { free(fbytes); free(slot); free(bri); free(padb); return -1; }
         total_slots += (size_t)slot[i];
     }
     /* main-data stream (all slots concatenated) */
@@ -518,6 +531,9 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
                 mode_ext = (ms ? 2 : 0) | (is ? 1 : 0);
             }
         }
+        /* mode_extension is "don't care" outside joint stereo, but the reference tests its bits in every mode
+         * (HDR_TEST_I_STEREO / HDR_TEST_MS_STEREO, minimp3.d:100-103); for stereo only with tied block types (see below) */
+        if (p->mode_ext_any && mode != 1 && (nch == 1 || p->stereo_mode >= 2)) mode_ext = (int)rng_below(&vrng, 4);
         hdr3[fi] = (uint8_t)((mode << 6) | (mode_ext << 4) | (p->emphasis_bits & 0xF));
         if (p->private_bits) priv[fi] = (uint8_t)rng_below(&rng, nch == 1 ? 32 : 8);
 
@@ -572,7 +588,7 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
         }
         slot_start += (size_t)slot[fi];
         if (((mw.pos + 7) >> 3) > slot_start) { /* internal error: overran the slot */
-            free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3); free(priv);
+            free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3); free(priv); free(bri); free(padb);
             return -2;
         }
     }
@@ -581,7 +597,7 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
     size_t o = 0;
     size_t need = (size_t)p->id3v2_bytes + (p->id3v1 ? 128 : 0);
     for (size_t i = 0; i < nfr; i++) need += (size_t)fbytes[i];
-    if (need > cap) { free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3); free(priv); return -3; }
+    if (need > cap) { free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3); free(priv); free(bri); free(padb); return -3; }
     memset(out, 0, need);
     if (p->id3v2_bytes >= 10) {
         int body = p->id3v2_bytes - 10;
@@ -595,8 +611,7 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
         uint8_t* h = out + o;
         h[0] = 0xFF;
         h[1] = (uint8_t)((f.mpeg25 ? 0xE0 : 0xF0) | (f.mpeg1 ? 0x08 : 0x00) | 0x02 | (p->crc ? 0 : 1));
-        int pad = fbytes[fi] - (int)(num / p->hz);
-        h[2] = (uint8_t)((f.br_idx << 4) | (f.sr_code << 2) | (pad << 1));
+        h[2] = (uint8_t)((bri[fi] << 4) | (f.sr_code << 2) | (padb[fi] << 1));
         h[3] = hdr3[fi];
         size_t q = 4;
         if (p->crc) { h[4] = 0xAB; h[5] = 0xCD; q = 6; } /* never verified by the reference (minimp3.d:1533-1536) */
@@ -618,6 +633,6 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
         info_out->mpeg1 = f.mpeg1;
         info_out->sr_idx = f.sr_idx;
     }
-    free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3); free(priv);
+    free(fbytes); free(slot); free(md); free(mdb_of); free(plans); free(hdr3); free(priv); free(bri); free(padb);
     return (long long)o;
 }

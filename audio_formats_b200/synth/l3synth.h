@@ -30,6 +30,8 @@ typedef struct {
     int emphasis_bits; /* low 4 bits of header byte 3 (copyright/original/emphasis) */
     int mixed_only_short; /* 1: mixed_block_flag only on the short blocks of a mixed run, not on its start/stop blocks */
     int free_format;   /* 1: write bitrate index 0 (free format); bitrate_kbps may then be any value (frame <= 2304 bytes) */
+    int vbr;           /* 1: the bitrate index and the padding bit change from frame to frame (around bitrate_kbps) */
+    int mode_ext_any;  /* 1: random mode_extension bits in frames that are not joint stereo (mono; stereo needs stereo_mode >= 2) */
     int private_bits;  /* 1: random private bits (MPEG-1: the reference takes them for granule 0's scfsi; the stream is written the way the reference reads it) */
 } l3s_params_t;
 

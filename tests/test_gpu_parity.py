@@ -94,6 +94,27 @@ def test_private_bits_leak_into_scfsi(ctx, hz, nch, rate):
     check_stream(ctx, synth.generate(p, want_quantised=True), f"private bits {hz} {nch}ch")
 
 
+@pytest.mark.parametrize("hz,nch,rate", [(44100, 2, 128), (48000, 1, 96), (22050, 2, 64), (32000, 2, 224), (11025, 1, 24)])
+def test_vbr(ctx, hz, nch, rate):
+    """Bitrate index and padding bit change from frame to frame (allowed by hdr_compare, minimp3.d:241-247)."""
+    from audio_formats_b200 import synth
+    p = synth.SynthParams(seed=600 + hz // 100 + nch, hz=hz, nch=nch, bitrate_kbps=rate, nframes=160, vbr=1, scfsi=1,
+                          block_mode=1 if hz >= 32000 else 2, stereo_mode=2 if nch == 2 else 0, reservoir=2,
+                          small_scalefactors=0)
+    check_stream(ctx, synth.generate(p, want_quantised=True), f"vbr {hz} {nch}ch")
+
+
+@pytest.mark.parametrize("hz,nch,rate,sm", [(44100, 1, 64, 0), (22050, 1, 32, 0), (48000, 1, 96, 0), (44100, 2, 128, 2), (22050, 2, 64, 2)])
+def test_mode_extension_bits_outside_joint_stereo(ctx, hz, nch, rate, sm):
+    """mode_extension is "don't care" outside joint stereo, but the reference tests its bits in every mode
+    (minimp3.d:100-103): an MPEG-1 mono frame with the intensity bit goes silent, an MPEG-2 one is scaled by sqrt(2)
+    when the MS bit is set as well, plain-stereo frames get intensity processing.  Same here."""
+    from audio_formats_b200 import synth
+    p = synth.SynthParams(seed=700 + hz // 100 + nch, hz=hz, nch=nch, bitrate_kbps=rate, nframes=120, mode_ext_any=1,
+                          stereo_mode=sm, block_mode=1 if hz >= 32000 else 2, small_scalefactors=0, reservoir=1)
+    check_stream(ctx, synth.generate(p, want_quantised=True), f"mode_ext {hz} {nch}ch")
+
+
 def test_config5_320kbps(ctx):
     from audio_formats_b200 import synth
     check_stream(ctx, synth.generate(synth.config5_params(5, 6.0), want_quantised=True), "config5")
@@ -203,5 +224,5 @@ def test_random_generator_profiles(ctx, seed):
                           small_scalefactors=int(rng.integers(0, 2)), table_cycle=int(rng.integers(0, 2)),
                           table_cycle_pos=seed, no_padding=int(rng.integers(0, 2)),
                           id3v2_bytes=int(rng.choice([0, 0, 10, 777])), id3v1=int(rng.integers(0, 2)),
-                          mixed_only_short=int(seed % 3 == 0), private_bits=int(seed % 4 == 1))
+                          mixed_only_short=int(seed % 3 == 0), private_bits=int(seed % 4 == 1), vbr=int(seed % 5 == 2), mode_ext_any=int(seed % 7 == 3))
     check_stream(ctx, synth.generate(p, want_quantised=True), f"random[{seed}] {p}")

@@ -52,6 +52,16 @@ def test_free_format(built, hz, nch, kbps, nopad):
     assert pcm.shape[0] == st.frames * st.samples_per_frame
 
 
+@pytest.mark.parametrize("hz,nch,rate", [(44100, 2, 128), (48000, 1, 96), (22050, 2, 64), (11025, 1, 24)])
+def test_vbr(built, hz, nch, rate):
+    from audio_formats_b200 import synth
+    p = synth.SynthParams(seed=90 + nch, hz=hz, nch=nch, bitrate_kbps=rate, nframes=80, vbr=1, reservoir=2,
+                          block_mode=1 if hz >= 32000 else 2)
+    st = synth.generate(p)
+    sc, pcm, taps = scan_vs_oracle(st.data, f"vbr {hz} {nch}")
+    assert sc.granules == len(taps) == st.granules and pcm.shape[0] == st.frames * st.samples_per_frame
+
+
 @pytest.mark.parametrize("nch", [1, 2])
 def test_private_bits(built, nch):
     """Private bits set (they become granule 0's scfsi nibble in the reference): same frames, same lengths."""

@@ -79,6 +79,17 @@ def test_short_and_mixed_blocks(built, hz, nch, rate):
     assert d <= TOL, f"{p}: max |oracle - ffmpeg| = {d:.3e}"
 
 
+@pytest.mark.parametrize("hz,nch,rate", [(44100, 2, 128), (48000, 1, 96), (22050, 2, 64), (32000, 2, 224), (11025, 1, 24)])
+def test_vbr(built, hz, nch, rate):
+    """Bitrate index and padding bit changing from frame to frame, heavy reservoir across frames of different size."""
+    from audio_formats_b200 import synth
+    p = synth.SynthParams(seed=11, hz=hz, nch=nch, bitrate_kbps=rate, nframes=120, vbr=1, block_mode=1 if hz >= 32000 else 2,
+                          scfsi=1, small_scalefactors=0, stereo_mode=1 if nch == 2 else 0, reservoir=2)
+    _, _, got, ref = decode_both(p)
+    d = np.abs(got.astype(np.float64) - ref).max()
+    assert d <= TOL, f"{p}: max |oracle - ffmpeg| = {d:.3e}"
+
+
 @pytest.mark.parametrize("hz,rate", [(44100, 128), (48000, 160), (32000, 96)])
 def test_intensity_stereo_mpeg1(built, hz, rate):
     """MS + intensity joint stereo on long blocks (pan table, illegal position 7, MS fallback).  Granules where only
