@@ -80,6 +80,33 @@ def test_tags_and_crc(built):
     scan_vs_oracle(synth.generate(p).data, "tags")
 
 
+def _ape_tag(item_bytes: int) -> bytes:
+    """APEv2 tag: 32-byte header, items, 32-byte footer; the size field counts items + footer, and the reference removes
+    32 + size bytes (minimp3_ex.d:102-108), i.e. exactly a tag that has its header."""
+    size = item_bytes + 32
+    def block(flags):
+        return b"APETAGEX" + (2000).to_bytes(4, "little") + size.to_bytes(4, "little") + (1).to_bytes(4, "little") + \
+               flags.to_bytes(4, "little") + bytes(8)
+    return block(0xA0000000) + bytes((i * 37) & 0xFF for i in range(item_bytes)) + block(0x80000000)
+
+
+@pytest.mark.parametrize("variant", ["ape", "ape+id3v1", "id3v1+ext", "id3v2-footer", "all"])
+def test_trailing_and_leading_tags(built, variant):
+    """ID3v1, its 227-byte "TAG+" extension, APEv2 footers and an ID3v2 tag with a footer are all skipped the way the
+    reference skips them (minimp3_ex.d:93-142), including the order in which the trailing ones are tested."""
+    from audio_formats_b200 import synth
+    st = synth.generate(replace(synth.config3_params(31, 1.5), crc=0))
+    body = st.data
+    id3v1 = b"TAG" + bytes(125)
+    ext = b"TAG+" + bytes(223)
+    id3v2f = b"ID3\x04\x00\x10" + bytes([0, 0, 2, 0]) + bytes(256) + b"3DI\x04\x00\x10" + bytes([0, 0, 2, 0])
+    data = {"ape": body + _ape_tag(300), "ape+id3v1": body + _ape_tag(77) + id3v1, "id3v1+ext": body + ext + id3v1,
+            "id3v2-footer": id3v2f + body, "all": id3v2f + body + _ape_tag(500) + ext + id3v1}[variant]
+    sc, pcm, taps = scan_vs_oracle(data, variant)
+    assert sc.granules == st.granules == len(taps)          # every frame still decodes: nothing of a tag was taken for audio
+    assert pcm.shape[0] == st.frames * st.samples_per_frame
+
+
 def test_first_frames_without_reservoir_are_skipped(built):
     """Cutting the head off a stream leaves frames whose main_data_begin points before the cut: they emit no PCM
     and do not count in the length (minimp3.d:1546-1556, minimp3_ex.d:613-619)."""
