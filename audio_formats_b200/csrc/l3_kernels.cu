@@ -411,8 +411,14 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             // band gains (minimp3.d:714-719) come ready-made in the scalefactor record (l3_scf_kernel)
             const float* const scf0 = reinterpret_cast<const float*>(rec0 + kSfGainOff);
             const float* const scf1 = reinterpret_cast<const float*>(rec1 + kSfGainOff);
-            if (istereo)
-                for (int i = lane; i < 40; i += 32) W.ist[i] = rec1[40 + i];
+            if (istereo) {
+                // ist_pos is per-FRAME scratch in the reference (zeroed at frame start, minimp3.d:1497): what granule 1 of
+                // channel 1 does not transmit keeps granule 0's values, including the top-band entries that granule 0's
+                // L3_intensity_stereo wrote (minimp3.d:974-980).  W.ist still holds exactly that state.
+                const int n_sent = !d1.second_granule() ? 0 : (kind1 == 0 ? 21 : (kind1 == 1 ? 36 : 35));   // MPEG-1 partition totals
+                for (int i = lane; i < 40; i += 32)
+                    if (!d1.second_granule() || i < n_sent) W.ist[i] = rec1[40 + i];
+            }
             __syncwarp();
 
             // ---------------- requantisation (minimp3.d:813-816, 846, 874-878) + MS stereo (:885-896) -------

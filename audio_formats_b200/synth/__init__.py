@@ -30,7 +30,7 @@ class _Params(C.Structure):
                 ("scfsi", C.c_int), ("crc", C.c_int), ("escapes", C.c_int), ("gain_base", C.c_int),
                 ("level", C.c_double), ("small_scalefactors", C.c_int), ("table_cycle", C.c_int),
                 ("table_cycle_pos", C.c_int), ("no_padding", C.c_int), ("id3v2_bytes", C.c_int), ("id3v1", C.c_int),
-                ("emphasis_bits", C.c_int), ("mixed_only_short", C.c_int), ("free_format", C.c_int), ("vbr", C.c_int), ("mode_ext_any", C.c_int), ("private_bits", C.c_int)]
+                ("emphasis_bits", C.c_int), ("mixed_only_short", C.c_int), ("free_format", C.c_int), ("vbr", C.c_int), ("mode_ext_any", C.c_int), ("istereo_untied", C.c_int), ("private_bits", C.c_int)]
 
 
 class _Info(C.Structure):
@@ -79,6 +79,7 @@ class SynthParams:
     free_format: int = 0
     vbr: int = 0
     mode_ext_any: int = 0
+    istereo_untied: int = 0
     private_bits: int = 0
 
     @staticmethod

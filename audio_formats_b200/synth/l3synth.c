@@ -533,7 +533,7 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
         }
         /* mode_extension is "don't care" outside joint stereo, but the reference tests its bits in every mode
          * (HDR_TEST_I_STEREO / HDR_TEST_MS_STEREO, minimp3.d:100-103); for stereo only with tied block types (see below) */
-        if (p->mode_ext_any && mode != 1 && (nch == 1 || p->stereo_mode >= 2)) mode_ext = (int)rng_below(&vrng, 4);
+        if (p->mode_ext_any && mode != 1 && (nch == 1 || (p->stereo_mode >= 2 && !p->istereo_untied))) mode_ext = (int)rng_below(&vrng, 4);
         hdr3[fi] = (uint8_t)((mode << 6) | (mode_ext << 4) | (p->emphasis_bits & 0xF));
         if (p->private_bits) priv[fi] = (uint8_t)rng_below(&rng, nch == 1 ? 32 : 8);
 
@@ -553,7 +553,7 @@ long long l3s_generate(const l3s_params_t* p, uint8_t* out, size_t cap, int16_t*
             int zero_above[2] = {-1, -1};
             int bt[2], mx[2];
             for (int ch = 0; ch < nch; ch++) bt[ch] = next_block_type(p, &cs, &rng, ch, &mx[ch]);
-            if (nch == 2 && p->stereo_mode >= 2) {
+            if (nch == 2 && p->stereo_mode >= 2 && !p->istereo_untied) {
                 /* With intensity stereo the reference walks channel 0's band layout over channel 1's ist_pos
                  * array (minimp3.d:963-981); if channel 0 has more bands than channel 1 transmitted it reads
                  * uninitialised scratch (UB upstream).  Encoders that use intensity stereo keep both channels

@@ -32,6 +32,9 @@ typedef struct {
     int free_format;   /* 1: write bitrate index 0 (free format); bitrate_kbps may then be any value (frame <= 2304 bytes) */
     int vbr;           /* 1: the bitrate index and the padding bit change from frame to frame (around bitrate_kbps) */
     int mode_ext_any;  /* 1: random mode_extension bits in frames that are not joint stereo (mono; stereo needs stereo_mode >= 2) */
+    int istereo_untied; /* 1: with intensity stereo the two channels still choose their block types independently (the
+                         * reference then reads ist_pos entries channel 1 did not transmit: zero in granule 0, granule 0's
+                         * leftovers in granule 1 -- defined in D, whose locals start zeroed) */
     int private_bits;  /* 1: random private bits (MPEG-1: the reference takes them for granule 0's scfsi; the stream is written the way the reference reads it) */
 } l3s_params_t;
 

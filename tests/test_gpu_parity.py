@@ -115,6 +115,17 @@ def test_mode_extension_bits_outside_joint_stereo(ctx, hz, nch, rate, sm):
     check_stream(ctx, synth.generate(p, want_quantised=True), f"mode_ext {hz} {nch}ch")
 
 
+@pytest.mark.parametrize("hz,rate,seed", [(44100, 128, 1), (48000, 160, 2), (32000, 96, 3), (22050, 64, 4), (44100, 192, 5)])
+def test_intensity_stereo_with_untied_block_types(ctx, hz, rate, seed):
+    """Intensity stereo walks channel 0's band layout over channel 1's ist_pos array.  When the channels use different
+    block types it reads entries channel 1 never transmitted: zeros in granule 0, granule 0's leftovers (and the top-band
+    entries granule 0's intensity pass wrote) in granule 1 -- the array is per-frame scratch in the reference."""
+    from audio_formats_b200 import synth
+    p = synth.SynthParams(seed=800 + seed, hz=hz, nch=2, bitrate_kbps=rate, nframes=200, stereo_mode=2, istereo_untied=1,
+                          block_mode=1, small_scalefactors=0, reservoir=1, scfsi=1)
+    check_stream(ctx, synth.generate(p, want_quantised=True), f"untied intensity {hz}")
+
+
 def test_config5_320kbps(ctx):
     from audio_formats_b200 import synth
     check_stream(ctx, synth.generate(synth.config5_params(5, 6.0), want_quantised=True), "config5")
