@@ -54,7 +54,7 @@ def test_check_seeking_list(ctx):
     s.close()
 
 
-@pytest.mark.parametrize("cfg", ["c3", "lsf_mono", "mono48"])
+@pytest.mark.parametrize("cfg", ["c3", "lsf_mono", "mono48", "vbr", "vbr_lsf", "free_format", "private_bits"])
 def test_seek_then_read_matches_oracle_stream(ctx, cfg):
     import audio_formats_b200 as af
     import oracle
@@ -62,7 +62,12 @@ def test_seek_then_read_matches_oracle_stream(ctx, cfg):
     p = {"c3": synth.config3_params(33, 6.0),
          "lsf_mono": synth.SynthParams.for_seconds(6.0, hz=22050, seed=34, nch=1, bitrate_kbps=64, block_mode=1,
                                                   reservoir=2, small_scalefactors=0),
-         "mono48": synth.SynthParams.for_seconds(5.0, hz=48000, seed=35, nch=1, bitrate_kbps=96, reservoir=2)}[cfg]
+         "mono48": synth.SynthParams.for_seconds(5.0, hz=48000, seed=35, nch=1, bitrate_kbps=96, reservoir=2),
+         "vbr": synth.SynthParams.for_seconds(6.0, seed=36, bitrate_kbps=160, vbr=1, block_mode=1, stereo_mode=2, reservoir=2),
+         "vbr_lsf": synth.SynthParams.for_seconds(6.0, hz=24000, seed=37, bitrate_kbps=64, vbr=1, block_mode=2, reservoir=2),
+         "free_format": synth.SynthParams.for_seconds(5.0, seed=38, bitrate_kbps=210, free_format=1, block_mode=1, reservoir=2),
+         "private_bits": synth.SynthParams.for_seconds(5.0, seed=39, bitrate_kbps=128, private_bits=1, scfsi=1, block_mode=1,
+                                                      stereo_mode=1, reservoir=2)}[cfg]
     st = synth.generate(p)
     s = af.AudioStream(ctx).openFromMemory(st.data)
     o = oracle.OracleStream(st.data)
