@@ -330,8 +330,11 @@ __device__ __noinline__ void imdct_split(float2* x, float2* ovl, float2* y, bool
 }
 __device__ __forceinline__ void imdct_split(float*, float*, float*, bool, bool, int, int) {}
 
+#ifndef L3B_GRANULE_WARPS_PER_SM
+#define L3B_GRANULE_WARPS_PER_SM 16
+#endif
 template <int NCH, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
+__global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
     typedef VT<NCH> V;
     typedef typename V::T T;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -625,6 +628,8 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                     }
                 }
             }
+            __syncwarp();  // every lane has its inputs in registers: the buffer may be rewritten in the padded (x19) layout,
+                           // and the stores below are free to interleave with the transform
             const int aa0 = kind0 == 0 ? 31 : nlb0 - 1, aa1 = kind1 == 0 ? 31 : nlb1 - 1;
             if (aa0 > 0 || aa1 > 0) {
                 const bool lo0 = lane >= 1 && lane - 1 < aa0, up0 = lane < aa0;
@@ -666,7 +671,6 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
 #pragma unroll
                 for (int i = 0; i < 9; i++) ovl[i] = oc[i];
             }
-            __syncwarp();  // every lane has consumed its inputs; the buffer is reused in the padded (x19) layout
             if (mode >= 1) {
                 const uint32_t fm = (lane & 1) ? 0x80000000u : 0u;   // L3_change_sign: odd samples of odd bands
 #pragma unroll
