@@ -107,6 +107,7 @@ def load_library():
         "l3b_scan_maindata": (vp, [vp]),
         "l3b_scan_descs": (vp, [vp]),
         "l3b_scan_fill_stream_desc": (None, [vp, C.POINTER(StreamDesc)]),
+        "l3b_scans_assemble": (C.c_int, [C.POINTER(vp), C.c_uint32, vp, C.c_uint64, vp, C.c_uint64, vp, C.POINTER(Batch)]),
         "l3b_decode_scans": (C.c_int, [vp, C.POINTER(vp), C.c_uint32, C.POINTER(vp), C.POINTER(C.c_int32)]),
         "l3b_stream_open_memory": (C.c_int, [vp, u8p, C.c_size_t, C.POINTER(vp)]),
         "l3b_stream_open_file": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
@@ -262,6 +263,33 @@ class HostBatch:
     def __init__(self, scans: Sequence[Scan], want_taps: bool = False, replicate: int = 1, staging: "PinnedBuffer | None" = None):
         self.scans = list(scans)
         self.want_taps = want_taps
+        if replicate == 1 and self.scans:
+            # assembled inside the library (l3b_scans_assemble): plain memcpys with the GIL released, so that the lanes
+            # of a BatchPipeline build their waves in parallel
+            L = load_library()
+            n = len(self.scans)
+            hs = (C.c_void_p * n)(*[sc._h for sc in self.scans])
+            b = Batch()
+            rc = L.l3b_scans_assemble(hs, n, None, 0, None, 0, None, C.byref(b))
+            if rc:
+                raise L3BError(rc, "l3b_scans_assemble (size query)")
+            nb, nd = int(b.maindata_bytes), int(b.n_grch)
+            doff = (nb + 63) & ~63
+            if staging is not None and doff + 16 * nd + 64 <= staging.nbytes:
+                self.blob = staging.u8[:nb]
+                self.descs = staging.u8[doff:doff + 16 * nd].view(GRCH_DTYPE)
+            else:
+                self.blob = np.empty(nb, np.uint8)
+                self.descs = np.empty(nd, GRCH_DTYPE)
+            sd = np.zeros(n, dtype=STREAM_DTYPE)
+            rc = L.l3b_scans_assemble(hs, n, self.blob.ctypes.data, nb, self.descs.ctypes.data, nd, sd.ctypes.data, C.byref(b))
+            if rc:
+                raise L3BError(rc, "l3b_scans_assemble")
+            self.streams = sd
+            self.pcm_floats = int(b.pcm_floats)
+            self.n_grch = nd
+            self._taps = Taps()
+            return
         blobs, descs = [], []
         sd = np.zeros(len(scans) * replicate, dtype=STREAM_DTYPE)
         off = grch = pcm = 0

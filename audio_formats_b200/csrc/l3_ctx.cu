@@ -478,6 +478,47 @@ int l3b_decode_batch(l3b_ctx_t* c, const l3b_batch_t* b) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// layer 2: the decode program of a set of scanned streams, assembled into caller-owned memory
+int l3b_scans_assemble(l3b_scan_t* const* scans, uint32_t n, uint8_t* blob, uint64_t blob_cap, l3b_grch_desc_t* descs,
+                       uint64_t desc_cap, l3b_stream_desc_t* streams, l3b_batch_t* batch) {
+    if (!scans || !n || !batch) return L3B_E_PARAM;
+    uint64_t n_desc = 0, n_blob = 0, pcm_total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!scans[i]) return L3B_E_PARAM;
+        n_desc += scans[i]->r.prog.descs.size();
+        n_blob += ((scans[i]->r.prog.blob.size() + 15) & ~(size_t)15) + 16;
+        pcm_total = ((pcm_total + 3) & ~(uint64_t)3) + scans[i]->r.pcm_count;
+    }
+    memset(batch, 0, sizeof *batch);
+    batch->maindata_bytes = n_blob;
+    batch->n_grch = n_desc;
+    batch->n_streams = n;
+    batch->pcm_floats = pcm_total;
+    if (!blob && !descs && !streams) return 0;   // size query
+    if (!blob || !descs || !streams || blob_cap < n_blob || desc_cap < n_desc) return L3B_E_PARAM;
+    uint64_t boff = 0, doff = 0, poff = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const ScanResult& s = scans[i]->r;
+        l3b_scan_fill_stream_desc(scans[i], &streams[i]);
+        streams[i].maindata_off = boff;
+        streams[i].first_grch = doff;
+        poff = (poff + 3) & ~(uint64_t)3;   // 16-byte aligned PCM rows (stereo stores are 8-byte vectors)
+        streams[i].pcm_off = poff;
+        poff += s.pcm_count;
+        const size_t nb = s.prog.blob.size(), padded = ((nb + 15) & ~(size_t)15) + 16;
+        if (nb) memcpy(blob + boff, s.prog.blob.data(), nb);
+        memset(blob + boff + nb, 0, padded - nb);   // >= 16 zero bytes after every stream
+        boff += padded;
+        if (!s.prog.descs.empty()) memcpy(descs + doff, s.prog.descs.data(), s.prog.descs.size() * sizeof(l3b_grch_desc_t));
+        doff += s.prog.descs.size();
+    }
+    batch->maindata = blob;
+    batch->grch = descs;
+    batch->streams = streams;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // layer 2: the batch entry point over scanned streams
 int l3b_decode_scans(l3b_ctx_t* c, l3b_scan_t* const* scans, uint32_t n, float* const* pcm, int32_t* status) {
     if (!c || !scans || !n || !pcm) return L3B_E_PARAM;

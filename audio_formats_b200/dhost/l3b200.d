@@ -106,6 +106,8 @@ ulong l3b_scan_maindata_bytes(const(l3b_scan_t)* s);
 const(ubyte)* l3b_scan_maindata(const(l3b_scan_t)* s);
 const(l3b_grch_desc_t)* l3b_scan_descs(const(l3b_scan_t)* s);
 void l3b_scan_fill_stream_desc(const(l3b_scan_t)* s, l3b_stream_desc_t* outDesc);
+int l3b_scans_assemble(l3b_scan_t** scans, uint n, ubyte* blob, ulong blobCap, l3b_grch_desc_t* descs, ulong descCap,
+                       l3b_stream_desc_t* streams, l3b_batch_t* batch);
 int l3b_decode_scans(l3b_ctx_t* ctx, l3b_scan_t** scans, uint n, float** pcm, int* status);
 
 int l3b_stream_open_memory(l3b_ctx_t* ctx, const(ubyte)* data, size_t size, l3b_stream_t** outStream);

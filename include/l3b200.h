@@ -147,6 +147,15 @@ const uint8_t* l3b_scan_maindata(const l3b_scan_t* s);
 const l3b_grch_desc_t* l3b_scan_descs(const l3b_scan_t* s);
 void l3b_scan_fill_stream_desc(const l3b_scan_t* s, l3b_stream_desc_t* out); /* offsets left 0 */
 
+/* Assemble the decode program of n scanned streams -- what the D host's batch entry point hands to the shim -- into
+ * caller-owned (ideally pinned) memory: `blob` receives the main data of the streams back to back, each 16-byte aligned
+ * and followed by >= 16 zero bytes; `descs` the granule-channel descriptors; `streams` the stream table with its offsets
+ * filled in (PCM rows 16-byte aligned).  `*batch` is filled to describe them (pcm = NULL).  Sizes: pass NULL buffers to
+ * get the required blob bytes / descriptor count / PCM floats in `*batch` without copying anything.
+ * Returns L3B_E_PARAM when a capacity is too small. */
+int l3b_scans_assemble(l3b_scan_t* const* scans, uint32_t n, uint8_t* blob, uint64_t blob_cap, l3b_grch_desc_t* descs,
+                       uint64_t desc_cap, l3b_stream_desc_t* streams, l3b_batch_t* batch);
+
 /* Batch entry point the D host adds next to AudioStream: decode n scanned streams in one go.
  * pcm[i] must have room for l3b_scan_delivered_samples(scans[i]) floats. */
 int l3b_decode_scans(l3b_ctx_t* ctx, l3b_scan_t* const* scans, uint32_t n, float* const* pcm, int32_t* status);
