@@ -8,6 +8,8 @@ SMs and the host cores work at the same time.  ctypes releases the GIL inside ev
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Sequence
@@ -48,6 +50,10 @@ class BatchPipeline:
         errors: list = []
         next_wave = [0]
 
+        prof = os.environ.get("L3B_PIPELINE_PROFILE") == "1"
+        phases = [[0.0] * 5 for _ in range(self.lanes)]   # scan, assemble, upload, run (issue), download (incl. kernels)
+        import time as _time
+
         def lane(k: int):
             ctx = self._ctxs[k]
             L = ctx._L
@@ -59,7 +65,9 @@ class BatchPipeline:
                     if w >= len(waves):
                         return
                     idxs = waves[w]
+                    t0 = _time.perf_counter()
                     scans = list(self._pool.map(api.Scan, [datas[i] for i in idxs]))   # host prepass
+                    t1 = _time.perf_counter()
                     need = sum(int(s._L.l3b_scan_maindata_bytes(s._h)) + 48 + 16 * s.granules * s.channels for s in scans) + 4096
                     if self._staging[k] is None or self._staging[k].nbytes < need:
                         if self._staging[k] is not None:
@@ -71,19 +79,37 @@ class BatchPipeline:
                         cursor[0] = base + hb.pcm_floats
                     if base + hb.pcm_floats > out.size:
                         raise ValueError("output buffer too small")
+                    t2 = _time.perf_counter()
                     ctx._check(L.l3b_batch_upload_reuse(ctx._h, C.byref(hb.c_batch()), C.byref(self._res[k])))
+                    t3 = _time.perf_counter()
                     ctx._check(L.l3b_batch_run(ctx._h, self._res[k]))
+                    t4 = _time.perf_counter()
                     ctx._check(L.l3b_batch_download(ctx._h, self._res[k], out.ctypes.data + 4 * base, 0, hb.pcm_floats))
+                    t5 = _time.perf_counter()
+                    if prof:
+                        for j, dt in enumerate((t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                            phases[k][j] += dt
                     for i, s, sd in zip(idxs, scans, hb.streams):
                         results[i] = (base + int(sd["pcm_off"]), int(sd["pcm_count"]) // s.channels, s.channels, s.samplerate)
             except Exception as e:  # noqa: BLE001
                 errors.append(e)
 
-        threads = [threading.Thread(target=lane, args=(k,)) for k in range(self.lanes)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
+        # A lane that comes back from a library call needs the GIL to issue the next one; with the default 5 ms switch
+        # interval it can wait that long behind a thread that is running bytecode, and the copy engine idles meanwhile.
+        old_interval = sys.getswitchinterval()
+        sys.setswitchinterval(float(os.environ.get("L3B_PIPELINE_SWITCH_INTERVAL", "2e-4")))
+        try:
+            threads = [threading.Thread(target=lane, args=(k,)) for k in range(self.lanes)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+        finally:
+            sys.setswitchinterval(old_interval)
+        if prof:
+            tot = [sum(p[j] for p in phases) for j in range(5)]
+            print("pipeline profile, seconds summed over lanes: scan %.3f assemble %.3f upload %.3f run %.3f download %.3f" % tuple(tot),
+                  file=sys.stderr)
         if errors:
             raise errors[0]
         return results
