@@ -113,6 +113,13 @@ struct BitReader {
         int p = pos;
         pos += n;
         if (pos > limit) return 0;  // still advances
+        if (n == 0) return 0;
+        const int byte = p >> 3;
+        if (byte * 8 + 40 <= limit) {   // five whole bytes in range: one shift instead of a byte loop (n <= 32)
+            const uint64_t w = ((uint64_t)buf[byte] << 32) | ((uint64_t)buf[byte + 1] << 24) | ((uint64_t)buf[byte + 2] << 16) |
+                               ((uint64_t)buf[byte + 3] << 8) | (uint64_t)buf[byte + 4];
+            return (uint32_t)((w >> (40 - (p & 7) - n)) & ((1ull << n) - 1ull));
+        }
         uint32_t v = 0;
         while (n > 0) {
             int off = p & 7, take = 8 - off < n ? 8 - off : n;

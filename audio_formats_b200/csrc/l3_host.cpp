@@ -313,6 +313,10 @@ int scan_stream(const uint8_t* data, size_t size, ScanResult* out) {
     out->hz = oi.info.hz;
     out->length_frames = oi.info.channels ? oi.samples / oi.info.channels : 0;
 
+    // one allocation each instead of growth by doubling: the payloads are a little less than the file, and a frame of
+    // >= 24 bytes yields at most four descriptors
+    out->prog.blob.reserve(size + 64);
+    out->prog.descs.reserve(oi.index.size() * 4 + 16);
     Reader rd(data, size);
     rd.restart(oi.start_offset);
     int to_skip = oi.to_skip;
