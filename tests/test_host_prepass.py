@@ -160,3 +160,24 @@ def test_not_mp3(built):
         af.Scan(b"RIFF" + bytes(5000))
     with pytest.raises(af.L3BError):
         af.Scan(b"")
+
+
+def test_scans_assemble_matches_python_assembly(built):
+    """l3b_scans_assemble (the library builds a wave's blob, descriptors and stream table) == the numpy assembly."""
+    import audio_formats_b200 as af
+    from audio_formats_b200 import api, synth
+    streams = [synth.generate(synth.config4_params(s, 0.7)) for s in range(30, 41)]
+    scans = [af.Scan(st.data) for st in streams]
+    fast = api.HostBatch(scans)                                   # C path
+    slow = api.HostBatch(scans + [], replicate=2)                 # numpy path (two copies of the same set)
+    n = len(scans)
+    assert fast.n_grch * 2 == slow.n_grch and fast.blob.size * 2 == slow.blob.size
+    assert np.array_equal(fast.blob, slow.blob[:fast.blob.size])
+    assert np.array_equal(fast.descs, slow.descs[:fast.n_grch])
+    for name in fast.streams.dtype.names:
+        assert np.array_equal(fast.streams[name], slow.streams[name][:n]), name
+    assert fast.pcm_floats == int(slow.streams["pcm_off"][n - 1] + slow.streams["pcm_count"][n - 1])
+    # every stream is followed by >= 16 zero bytes and starts 16-byte aligned
+    for sd in fast.streams:
+        off, nb = int(sd["maindata_off"]), int(sd["maindata_bytes"])
+        assert off % 16 == 0 and not fast.blob[off + nb: off + nb + 16].any()
