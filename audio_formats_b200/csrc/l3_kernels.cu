@@ -43,23 +43,24 @@ void upload_constants() {
 // Shared memory per warp: spectrum T[608], DCT history T[33 rows x 33], small tables.  No block barriers.
 
 #ifdef L3B_EXP_NO_PHASE_SYNC
-#define L3B_PHASE_SYNC() ((void)0)
+#define L3B_PHASE_SYNC() __syncwarp()
 #else
 #define L3B_PHASE_SYNC() __syncthreads()
 #endif
 // the three barriers of a granule (after requantisation, after the IMDCT, after the DCT) can be dropped one by one
 #ifdef L3B_EXP_NO_SYNC1
-#define L3B_PHASE_SYNC1() ((void)0)
+#define L3B_PHASE_SYNC1() __syncwarp()
 #else
 #define L3B_PHASE_SYNC1() L3B_PHASE_SYNC()
 #endif
 #ifdef L3B_EXP_NO_SYNC2
-#define L3B_PHASE_SYNC2() ((void)0)
+#define L3B_PHASE_SYNC2() __syncwarp()
 #else
 #define L3B_PHASE_SYNC2() L3B_PHASE_SYNC()
 #endif
 #ifndef L3B_EXP_SYNC3   // measured (config 2): without the third barrier 19.57 ms, with it 19.69; dropping the first costs
-#define L3B_PHASE_SYNC3() ((void)0)   // 0.8 ms, the second 0.2 ms
+#define L3B_PHASE_SYNC3() __syncwarp()   // 0.8 ms, the second 0.2 ms.  (A dropped CTA barrier still has to order the warp's
+                                        // own shared-memory writes before the next stage's reads: __syncwarp.)
 #else
 #define L3B_PHASE_SYNC3() L3B_PHASE_SYNC()
 #endif
