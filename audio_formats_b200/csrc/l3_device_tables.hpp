@@ -108,6 +108,9 @@ inline HuffLut build_huff_lut() {
 //   c1code[t][6-bit peek] = len | flags<<4 | (len + popcount(flags))<<8       (minimp3.d:857-866)
 //   c1val[flags<<4 | s]   = the quad's two packed int16x2 words when the next four bits are s: sign bits are consumed
 //                           by the non-zero values in order v0..v3 (minimp3.d:869-878)
+#ifndef L3B_HUFF_ROOT_BITS
+#define L3B_HUFF_ROOT_BITS 9   // root-table width of the big_values books: measured entropy stage 8: 8.19 ms (18 KB of LUT), 9: 8.06 (27 KB), 10: 8.45 (43 KB, one CTA fewer per SM)
+#endif
 struct HuffLut32 {
     std::vector<uint32_t> entries;
     uint32_t base[L3_NBOOKS + 1];
@@ -147,7 +150,7 @@ inline void build_level32(int book, bool has_linbits, std::vector<uint32_t>& e, 
 inline HuffLut32 build_huff_lut32() {
     HuffLut32 L;
     for (int b = 0; b < L3_NBOOKS; b++) {
-        int rb = L3_BOOK_MAXLEN[b] < 8 ? L3_BOOK_MAXLEN[b] : 8;
+        int rb = L3_BOOK_MAXLEN[b] < L3B_HUFF_ROOT_BITS ? L3_BOOK_MAXLEN[b] : L3B_HUFF_ROOT_BITS;
         bool lin = false;
         for (int sel = 0; sel < 32; sel++) lin |= (L3_SEL2BOOK[sel] == b && L3_LINBITS[sel] != 0);
         L.base[b] = (uint32_t)L.entries.size();
