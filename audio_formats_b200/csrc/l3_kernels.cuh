@@ -1,11 +1,12 @@
 // l3_kernels.cuh -- device code of the Layer III granule decode path (sm_100a).
 //
-// Two kernels:
-//   l3_entropy_kernel   one thread per granule-channel: scalefactor decode + Huffman decode
-//                       (minimp3.d:613-644, 659-712, 748-883) -> signed 16-bit quantised spectra.
-//                       Integer work only; these are the "bit-exact spectral intermediates".
-//   l3_granule_kernel   one CTA (one warp per channel) per run of consecutive granules of one stream:
-//                       requantisation (minimp3.d:714-746, 813-816, 846), MS/intensity stereo (:885-982),
+// Kernels:
+//   l3_scf_kernel, l3_huff_big_kernel, l3_huff_c1_kernel   (l3_entropy.cu) scalefactor decode, band gains and Huffman
+//                       decode (minimp3.d:613-644, 659-719, 748-883) -> signed 16-bit quantised spectra + 256-byte
+//                       scalefactor/gain records.  Integer work (plus the gain products); the spectra are the
+//                       "bit-exact spectral intermediates".
+//   l3_granule_kernel   (l3_kernels.cu) one warp per run of consecutive granules of one stream:
+//                       requantisation (minimp3.d:727-746, 813-816, 846), MS/intensity stereo (:885-982),
 //                       short-block reorder (:984-1000), alias reduction (:1002-1020), IMDCT-36/12 with
 //                       overlap-add and frequency inversion (:1022-1168), DCT-32 matrixing (:1232-1298)
 //                       and the 512-tap window (:1305-1406), fused through shared memory and registers.
@@ -76,8 +77,8 @@ struct BatchParams {
     uint4* is;       // [n_grch][72] packed int16x8
     uint8_t* sf;     // [n_grch][96]
     float* pcm;
-    uint64_t grch_lo, grch_hi;  // granule-channel range the entropy kernel covers in this launch
-    int zero_fill;   // entropy kernel writes all 72 chunks (tap mode)
+    uint64_t grch_lo, grch_hi;  // granule-channel range the entropy kernels cover in this launch
+    int zero_fill;   // the count1 kernel zero-fills the chunks it does not reach (tap mode)
     HuffJob* jobs;        // [n_grch]
     const uint32_t* group_stream;   // [n_grch / 128 + 1] stream index of granule-channel 128 k (search hint)
     uint32_t* counters;   // work-distribution counters of the Huffman kernels: 2 per sub-batch, zeroed before every run

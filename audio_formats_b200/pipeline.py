@@ -1,7 +1,7 @@
 """Wave-pipelined batch decode: MP3 bytes in host memory -> float PCM in (pinned) host memory.
 
 The batch is cut into waves; `lanes` worker threads each own a GPU context (its own CUDA stream and a
-recycled device workspace) and run  host prepass -> H2D -> entropy kernel -> granule kernel -> D2H  for their
+recycled device workspace) and run  host prepass -> H2D -> entropy kernels -> granule kernel -> D2H  for their
 waves.  While one lane copies PCM back over PCIe the other lanes scan and decode, so the copy engine, the
 SMs and the host cores work at the same time.  ctypes releases the GIL inside every library call.
 """

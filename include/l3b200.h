@@ -122,8 +122,9 @@ int l3b_batch_download_taps(l3b_ctx_t* ctx, l3b_resident_t* r, const l3b_taps_t*
 void* l3b_batch_device_pcm(l3b_resident_t* r);                              /* raw device pointer (for checksums/tests) */
 void l3b_batch_free(l3b_ctx_t* ctx, l3b_resident_t* r);
 /* CUDA-event timing summed over the most recent `last_runs` calls of l3b_batch_run (at most 64 are kept;
- * synchronises the context).  A run is issued as sub-batches: entropy launches on one stream, granule launches on a
- * second stream as soon as their sub-batch's spectra exist, so the two kernels overlap.
+ * synchronises the context).  A run is issued as sub-batches (one by default): the entropy launches (scalefactor,
+ * big_values and count1 kernels) on one stream, the granule launches on a second stream as soon as their sub-batch's
+ * spectra exist.
  * ms[0] entropy launches (first start to last end), ms[1] sum of the granule launches' durations (measured in situ,
  * i.e. while sharing the GPU with later entropy launches), ms[2] whole run; *launches = kernels launched. */
 int l3b_batch_timing(l3b_ctx_t* ctx, int last_runs, float ms[3], int* launches);
