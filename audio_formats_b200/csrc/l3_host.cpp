@@ -187,9 +187,53 @@ int open_index(const uint8_t* data, size_t size, OpenInfo* oi, uint64_t from_off
         filled += io_read(kIoSize - kId3DetectSize);
     }
     if (filled < kBufSize) skip_id3v1(data + win, &filled);
+    // mp3d_find_frame accepts a header when the next ten headers, hopping by their own frame sizes, are compatible with
+    // it (minimp3.d:1436-1448).  Walking a clean stream frame by frame repeats nine of those ten checks every time.
+    // The memo below remembers, for the header expected next, that the nine behind it are already known to be valid
+    // and compatible, so only the tenth is looked at; anything unusual (free format, window end, a mismatch, a frame
+    // that does not start where expected) drops the memo and takes the full search, whose result is then the
+    // reference's by construction.
+    struct { bool valid = false; size_t next_abs = 0, tail_abs = 0; } memo;
+    auto full_search = [&](int* ffb, int* frame_size) {
+        const uint8_t* base = data + win + consumed;
+        const int bytes = (int)(filled - consumed);
+        int i = find_frame(base, bytes, ffb, frame_size);
+        memo.valid = false;
+        if (*frame_size && !Hdr(base + i).free_format()) {   // rebuild the memo: the ten hops from this header
+            const uint8_t* h = base + i;
+            int pos = 0, matched = 0;
+            for (; matched < kMaxSyncMatches; matched++) {
+                pos += Hdr(h + pos).frame_bytes(0) + Hdr(h + pos).padding();
+                if (i + pos + kHdrSize > bytes || !hdr_compatible(h, h + pos)) break;
+            }
+            if (matched == kMaxSyncMatches) {
+                memo.valid = true;
+                memo.next_abs = win + consumed + (size_t)i + (size_t)*frame_size;
+                memo.tail_abs = win + consumed + (size_t)i + (size_t)pos;
+            }
+        }
+        return i;
+    };
     for (;;) {
         int ffb = 0, frame_size = 0;
-        int i = find_frame(data + win + consumed, (int)(filled - consumed), &ffb, &frame_size);
+        int i;
+        const size_t here = win + consumed, win_end = win + filled;
+        bool fast = false;
+        if (memo.valid && memo.next_abs == here && memo.tail_abs + kHdrSize <= win_end && here + kHdrSize < win_end) {
+            const uint8_t* h = data + here;
+            const uint8_t* tail = data + memo.tail_abs;
+            const int fb = Hdr(h).frame_bytes(0), fb_pad = fb + Hdr(h).padding();
+            const size_t q11 = memo.tail_abs + (size_t)(Hdr(tail).frame_bytes(0) + Hdr(tail).padding());
+            // the eleventh header has to be inside the window (otherwise the reference's end-of-buffer rule decides: slow path)
+            if (fb && here + (size_t)fb_pad <= win_end && q11 + kHdrSize <= win_end && hdr_compatible(h, data + q11)) {
+                fast = true;
+                i = 0;
+                frame_size = fb_pad;
+                memo.next_abs = here + (size_t)fb_pad;
+                memo.tail_abs = q11;
+            }
+        }
+        if (!fast) i = full_search(&ffb, &frame_size);
         if (i && !frame_size) { consumed += i; continue; }
         if (!frame_size) break;
         const uint8_t* hdr = data + win + consumed + i;

@@ -154,6 +154,55 @@ def test_fault_injection(built, seed):
     scan_vs_oracle(bytes(b), f"fault{kind}")
 
 
+def _frame_offsets(data: bytes):
+    import oracle
+    L = oracle.lib()
+    pos, offs = 0, []
+    while pos + 4 <= len(data) and data[pos] == 0xFF and (data[pos + 1] & 0xE0) == 0xE0:
+        offs.append(pos)
+        pos += L.l3o_hdr_frame_bytes(data[pos:pos + 4], 0) + L.l3o_hdr_padding(data[pos:pos + 4])
+    return offs
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_header_level_fuzz(built, seed):
+    """Damage aimed at the frame headers of streams long enough for the 128 KiB window to slide: flipped header bits
+    (version, layer, bitrate, sample rate, padding, mode), a few garbage bytes between frames, a duplicated frame, frames
+    of another format spliced in.  The index pass verifies its ten-header sync chain incrementally; whatever it decides
+    has to be what the reference's frame-by-frame search decides (same length, same delivered samples, same granules)."""
+    from audio_formats_b200 import synth
+    rng = np.random.default_rng(4000 + seed)
+    p = synth.SynthParams(seed=300 + seed, nframes=int(rng.integers(330, 420)), bitrate_kbps=int(rng.choice([128, 192, 320])),
+                          vbr=int(seed % 3 == 0), block_mode=1, stereo_mode=1, reservoir=int(rng.integers(0, 3)))
+    st = synth.generate(p)
+    b = bytearray(st.data)
+    offs = _frame_offsets(st.data)
+    assert len(offs) == st.frames
+    kind = seed % 6
+    if kind == 0:      # flip header bits of several frames
+        for k in rng.choice(len(offs) - 2, 8, replace=False):
+            b[offs[k] + int(rng.integers(1, 4))] ^= 1 << int(rng.integers(0, 8))
+    elif kind == 1:    # a few garbage bytes between frames, at several places (back to front: offsets stay valid)
+        for k in sorted(rng.choice(len(offs) - 2, 5, replace=False), reverse=True):
+            b[offs[k]:offs[k]] = rng.integers(0, 256, int(rng.integers(1, 9)), dtype=np.uint8).tobytes()
+    elif kind == 2:    # duplicate a frame and drop another
+        k, j = sorted(int(x) for x in rng.choice(range(20, len(offs) - 20), 2, replace=False))
+        frame = bytes(b[offs[k]:offs[k + 1]])
+        del b[offs[j]:offs[j + 1]]
+        b[offs[k]:offs[k]] = frame
+    elif kind == 3:    # frames of another sample rate spliced in (the sync chain must refuse them)
+        other = synth.generate(synth.SynthParams(seed=9, hz=32000, nframes=30, bitrate_kbps=96)).data
+        k = int(rng.integers(50, len(offs) - 50))
+        b[offs[k]:offs[k]] = other[: len(other) // 2]
+    elif kind == 4:    # kill one header out of every ~40 so that chains end on a bad header again and again
+        for k in range(17, len(offs) - 2, 41):
+            b[offs[k]] = 0x00
+    else:              # cut the stream inside the last 16 KiB in several ways (end-of-buffer rule of the chain)
+        b = b[: offs[len(offs) - int(rng.integers(1, 12))] + int(rng.integers(0, 300))]
+    sc, pcm, taps = scan_vs_oracle(bytes(b), f"header fuzz {kind}/{seed}")
+    assert sc.granules == len(taps)
+
+
 def test_not_mp3(built):
     import audio_formats_b200 as af
     with pytest.raises(af.L3BError):
