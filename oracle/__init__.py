@@ -1,8 +1,8 @@
 """CPU oracle (TEST INFRASTRUCTURE ONLY) -- ctypes binding of oracle/libl3oracle.so.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
-this package.  The product (audio_formats_b200) never does.  PARITY UNPINNED against the D reference
-(see oracle/l3_oracle.h).
+this package.  The product (audio_formats_b200) never does.  PARITY UNPINNED against the D reference itself;
+cross-checked against FFmpeg's mp3float (see oracle/l3_oracle.h, tests/test_oracle_vs_ffmpeg.py).
 """
 from __future__ import annotations
 
