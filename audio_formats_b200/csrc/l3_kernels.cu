@@ -302,7 +302,9 @@ struct __align__(16) WarpSmem {
     // granule.  The current-granule rows ALIAS the spectrum buffer `xr` (natural layout while requantising,
     // x19 padded layout between IMDCT and DCT): each stage has consumed its input before the next one writes.
     typename VT<NCH>::T Dbuf[1 + 15 * kDStride + kXrStride];  // D = Dbuf + 1, so that row 15 (= xr) is 16-byte aligned
+#ifndef L3B_EXP_DIRECT_IS
     uint4 st_is[NCH * kIsChunks];              // TMA-staged inputs of the next granule: quantised spectra,
+#endif
     uint4 st_rec[NCH * kSfRecBytes / 16];      //   scalefactor records,
     uint4 st_desc[NCH];                        //   descriptors
     uint8_t sfbpair[3][288];
@@ -392,12 +394,18 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
     const int n_long_bands_mixed = 2 << (row == 1 ? 1 : 0);  // minimp3.d:1218
     const uint64_t skipf = S.pcm_skip / NCH, countf = S.pcm_count / NCH;   // in frames
     T* const pcm = reinterpret_cast<T*>(p.pcm + S.pcm_off);
+#ifdef L3B_EXP_DIRECT_IS
+    constexpr uint32_t kStageBytes = NCH * (kSfRecBytes + 16);   // experiment: spectra are read straight from global memory
+#else
     constexpr uint32_t kStageBytes = NCH * (kIsChunks * 16 + kSfRecBytes + 16);
+#endif
 
     auto prefetch = [&](int g) {  // lane 0: TMA bulk copies of granule g's inputs into the staging buffers
         const uint64_t di = S.first_grch + (uint64_t)g * NCH;
         mbar_expect_tx(&W.mbar, kStageBytes);
+#ifndef L3B_EXP_DIRECT_IS
         tma_load_1d(W.st_is, p.is + di * kIsChunks, NCH * kIsChunks * 16, &W.mbar);
+#endif
         tma_load_1d(W.st_rec, p.sf + di * kSfRecBytes, NCH * kSfRecBytes, &W.mbar);
         tma_load_1d(W.st_desc, p.grch + di, NCH * 16, &W.mbar);
     };
@@ -412,6 +420,19 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
         d1 = d0;
         int kind0 = 0, kind1 = 0, hb = 0;
         bool ms_frame = false, istereo = false;
+#ifdef L3B_EXP_DIRECT_IS
+        uint32_t gva[9], gvb[9];
+        const uint32_t* const gis = reinterpret_cast<const uint32_t*>(p.is + (S.first_grch + (uint64_t)g * NCH) * kIsChunks);
+        if (act) {
+#pragma unroll
+            for (int m = 0; m < 9; m++) {
+                gva[m] = __ldg(gis + lane + 32 * m);
+                gvb[m] = NCH == 2 ? __ldg(gis + kIsChunks * 4 + lane + 32 * m) : 0u;
+            }
+            if (it + 1 < n_iter && lane < NCH * 9)   // next granule's rows into L2: 9 lines of 128 bytes per channel
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(gis) + NCH * kIsChunks * 16 + lane * 128));
+        }
+#endif
         if (act) {
             mbar_wait(&W.mbar, it & 1);
             {
@@ -450,7 +471,11 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
             {
                 const int nch0 = *reinterpret_cast<const uint16_t*>(rec0 + 80);
                 const int nch1 = *reinterpret_cast<const uint16_t*>(rec1 + 80);
+#ifdef L3B_EXP_DIRECT_IS
+                const uint32_t* isw0 = gis;
+#else
                 const uint32_t* isw0 = reinterpret_cast<const uint32_t*>(W.st_is);
+#endif
                 const uint32_t* isw1 = isw0 + (NCH - 1) * (kIsChunks * 4);
                 const bool ms_now = NCH == 2 && ms_frame && !istereo;
                 const int nz_hi = max(nch0, NCH == 2 ? nch1 : 0);   // chunks (8 coefficients) holding anything non-zero
@@ -470,8 +495,13 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                         else *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(0.0f, 0.0f);
                         continue;
                     }
+#ifdef L3B_EXP_DIRECT_IS
+                    const uint32_t va = (pi >> 2) < nch0 ? gva[m] : 0u;
+                    const uint32_t vb = (NCH == 2 && (pi >> 2) < nch1) ? gvb[m] : 0u;
+#else
                     const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;   // chunks past nz_chunks were never written
                     const uint32_t vb = (NCH == 2 && (pi >> 2) < nch1) ? isw1[pi] : 0u;
+#endif
                     const float sa = scf0[W.sfbpair[kind0][pi]];
                     const float sb = NCH == 2 ? scf1[W.sfbpair[kind1][pi]] : 0.0f;
                     // a 16-bit value lies in [-128, 127] iff its bits 15..7 are all equal
