@@ -43,15 +43,31 @@ class StreamDesc(C.Structure):
 
 
 class Taps(C.Structure):
-    _fields_ = [("is_", C.c_void_p), ("iscf", C.c_void_p), ("ist_pos", C.c_void_p)]
+    _fields_ = [("is_", C.c_void_p), ("iscf", C.c_void_p), ("ist_pos", C.c_void_p),
+                ("xr", C.c_void_p), ("st", C.c_void_p), ("im", C.c_void_p), ("dct", C.c_void_p)]
+
+
+OUT_S16, MATH_FUSED = 1, 2   # l3b_batch_t.flags
 
 
 class Batch(C.Structure):
     _fields_ = [("maindata", C.c_void_p), ("maindata_bytes", C.c_uint64), ("grch", C.c_void_p), ("n_grch", C.c_uint64),
                 ("streams", C.c_void_p), ("n_streams", C.c_uint32), ("pcm", C.c_void_p), ("pcm_floats", C.c_uint64),
-                ("status", C.c_void_p), ("taps", C.c_void_p)]
+                ("status", C.c_void_p), ("taps", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class PipelineOpts(C.Structure):
+    _fields_ = [("lanes", C.c_int32), ("wave_streams", C.c_int32), ("scan_threads", C.c_int32), ("flags", C.c_uint32)]
+
+
+class StreamResult(C.Structure):
+    _fields_ = [("pcm_off", C.c_uint64), ("frames", C.c_uint64), ("channels", C.c_int32), ("samplerate", C.c_int32),
+                ("status", C.c_int32), ("device", C.c_int32)]
+
+
+PIPELINE_PHASES = 6
+READ_CB = C.CFUNCTYPE(C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)   # mp3dec_io_t.read, minimp3_ex.d:61-71
+SEEK_CB = C.CFUNCTYPE(C.c_int, C.c_uint64, C.c_void_p)                  # mp3dec_io_t.seek
 assert C.sizeof(GrchDesc) == 16 and C.sizeof(StreamDesc) == 56, (C.sizeof(GrchDesc), C.sizeof(StreamDesc))
 
 GRCH_DTYPE = np.dtype([("bit_start", "<u4"), ("w1", "<u4"), ("w2", "<u4"), ("w3", "<u4")])
@@ -82,6 +98,7 @@ def load_library():
         "l3b_ctx_destroy": (None, [vp]),
         "l3b_last_error": (C.c_char_p, [vp]),
         "l3b_host_alloc": (vp, [C.c_size_t]),
+        "l3b_host_alloc_near": (vp, [C.c_int, C.c_size_t]),
         "l3b_host_free": (None, [vp]),
         "l3b_decode_batch": (C.c_int, [vp, C.POINTER(Batch)]),
         "l3b_batch_upload": (C.c_int, [vp, C.POINTER(Batch), C.POINTER(vp)]),
@@ -109,8 +126,15 @@ def load_library():
         "l3b_scan_fill_stream_desc": (None, [vp, C.POINTER(StreamDesc)]),
         "l3b_scans_assemble": (C.c_int, [C.POINTER(vp), C.c_uint32, vp, C.c_uint64, vp, C.c_uint64, vp, C.POINTER(Batch)]),
         "l3b_decode_scans": (C.c_int, [vp, C.POINTER(vp), C.c_uint32, C.POINTER(vp), C.POINTER(C.c_int32)]),
+        "l3b_pipeline_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(PipelineOpts), C.POINTER(vp)]),
+        "l3b_pipeline_destroy": (None, [vp]),
+        "l3b_pipeline_decode": (C.c_int, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_uint32, vp, C.c_uint64,
+                                          C.POINTER(StreamResult), C.POINTER(C.c_uint64)]),
+        "l3b_pipeline_profile": (C.c_int, [vp, C.POINTER(C.c_double * PIPELINE_PHASES)]),
+        "l3b_pipeline_last_error": (C.c_char_p, [vp]),
         "l3b_stream_open_memory": (C.c_int, [vp, u8p, C.c_size_t, C.POINTER(vp)]),
         "l3b_stream_open_file": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+        "l3b_stream_open_callbacks": (C.c_int, [vp, READ_CB, SEEK_CB, vp, C.POINTER(vp)]),
         "l3b_stream_close": (None, [vp]),
         "l3b_stream_num_channels": (C.c_int, [vp]),
         "l3b_stream_length_frames": (C.c_int64, [vp]),
@@ -231,10 +255,11 @@ class Context:
 class PinnedBuffer:
     """Page-locked host memory (cudaHostAlloc) viewed as a numpy array."""
 
-    def __init__(self, nbytes: int):
+    def __init__(self, nbytes: int, near_device: int | None = None):
         self._L = load_library()
         self.nbytes = int(nbytes)
-        self.ptr = self._L.l3b_host_alloc(self.nbytes)
+        # near_device: place the pages on the NUMA node that GPU hangs off (l3b_host_alloc_near)
+        self.ptr = self._L.l3b_host_alloc(self.nbytes) if near_device is None else self._L.l3b_host_alloc_near(near_device, self.nbytes)
         if not self.ptr:
             raise L3BError(E_MEMORY, f"cannot pin {nbytes} bytes of host memory")
         self.u8 = np.frombuffer((C.c_uint8 * self.nbytes).from_address(self.ptr), dtype=np.uint8)
@@ -260,9 +285,12 @@ class HostBatch:
     """A batch assembled on the host from scans (what the D host hands to the shim).
     `staging` (optional PinnedBuffer) receives the blob and the descriptors so the H2D copies read pinned memory."""
 
-    def __init__(self, scans: Sequence[Scan], want_taps: bool = False, replicate: int = 1, staging: "PinnedBuffer | None" = None):
+    def __init__(self, scans: Sequence[Scan], want_taps: bool = False, replicate: int = 1, staging: "PinnedBuffer | None" = None,
+                 flags: int = 0, float_taps: bool = False):
         self.scans = list(scans)
-        self.want_taps = want_taps
+        self.want_taps = want_taps or float_taps
+        self.float_taps = float_taps
+        self.flags = flags
         if replicate == 1 and self.scans:
             # assembled inside the library (l3b_scans_assemble): plain memcpys with the GIL released, so that the lanes
             # of a BatchPipeline build their waves in parallel
@@ -330,7 +358,12 @@ class HostBatch:
         b.pcm = pcm.ctypes.data if pcm is not None else None
         b.pcm_floats = self.pcm_floats
         b.status = None
+        if with_taps and self.float_taps:   # non-NULL float tap pointers make the library allocate the float tap buffers
+            self._ft = {k: np.zeros((self.n_grch, 576), np.float32) for k in ("xr", "st", "im", "dct")}
+            self._taps.xr, self._taps.st = self._ft["xr"].ctypes.data, self._ft["st"].ctypes.data
+            self._taps.im, self._taps.dct = self._ft["im"].ctypes.data, self._ft["dct"].ctypes.data
         b.taps = C.cast(C.pointer(self._taps), C.c_void_p) if with_taps else None
+        b.flags = self.flags
         return b
 
 
@@ -359,8 +392,9 @@ class ResidentBatch:
         return list(ms), n.value
 
     def download(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        """PCM samples [first, first + count): float32, or int16 when the batch was built with OUT_S16."""
         count = self.host.pcm_floats - first if count is None else count
-        out = np.empty(count, np.float32)
+        out = np.empty(count, np.int16 if self.host.flags & OUT_S16 else np.float32)
         self.ctx._check(self.ctx._L.l3b_batch_download(self.ctx._h, self._h, out.ctypes.data, first, count))
         return out
 
@@ -372,6 +406,14 @@ class ResidentBatch:
         t = Taps(is_.ctypes.data, iscf.ctypes.data, ist.ctypes.data)
         self.ctx._check(self.ctx._L.l3b_batch_download_taps(self.ctx._h, self._h, C.byref(t)))
         return is_, iscf, ist
+
+    def download_float_taps(self):
+        """Float stage snapshots {xr, st, im, dct}: [n_grch, 576] each (the batch must have been built with float_taps)."""
+        n = self.host.n_grch
+        arrs = {k: np.zeros((n, 576), np.float32) for k in ("xr", "st", "im", "dct")}
+        t = Taps(None, None, None, arrs["xr"].ctypes.data, arrs["st"].ctypes.data, arrs["im"].ctypes.data, arrs["dct"].ctypes.data)
+        self.ctx._check(self.ctx._L.l3b_batch_download_taps(self.ctx._h, self._h, C.byref(t)))
+        return arrs
 
     @property
     def device_pcm_ptr(self) -> int:
@@ -389,23 +431,40 @@ class ResidentBatch:
             pass
 
 
-def decode_batch_with_taps(ctx: Context, scans: Sequence[Scan]):
-    """Test helper: decode through l3b_decode_batch (host buffers in/out) and return
-    (list of pcm arrays, is[n_grch,576], iscf[n_grch,40], ist_pos[n_grch,40])."""
-    hb = HostBatch(scans, want_taps=True)
+def decode_batch_with_taps(ctx: Context, scans: Sequence[Scan], float_taps: bool = False):
+    """Test helper: decode a resident batch with taps and return
+    (list of pcm arrays, is[n_grch,576], iscf[n_grch,40], ist_pos[n_grch,40]) -- plus, with float_taps, a dict of the float
+    stage snapshots {xr, st, im, dct} [n_grch, 576] and the stream table (first_grch / pcm_skip locate the delivered granules)."""
+    hb = HostBatch(scans, want_taps=True, float_taps=float_taps)
     rb = ctx.upload(hb)
     try:
         rb.run()
         rb.sync()
         pcm = rb.download()
         taps = rb.download_taps()
+        ftaps = rb.download_float_taps() if float_taps else None
     finally:
         rb.free()
     outs = []
     for s, sdesc in zip(scans, hb.streams):
         off, n = int(sdesc["pcm_off"]), int(sdesc["pcm_count"])
         outs.append(pcm[off:off + n].reshape(-1, s.channels))
+    if float_taps:
+        return outs, *taps, ftaps, hb.streams
     return outs, *taps
+
+
+def decode_mode(ctx: Context, scans: Sequence[Scan], flags: int):
+    """Decode a batch in a given output / arithmetic mode (OUT_S16, MATH_FUSED); returns one [frames, channels] array per stream."""
+    hb = HostBatch(scans, flags=flags)
+    rb = ctx.upload(hb)
+    try:
+        rb.run()
+        rb.sync()
+        pcm = rb.download()
+    finally:
+        rb.free()
+    return [pcm[int(sd["pcm_off"]):int(sd["pcm_off"]) + int(sd["pcm_count"])].reshape(-1, s.channels) for s, sd in zip(scans, hb.streams)]
 
 
 class AudioStream:
@@ -440,6 +499,33 @@ class AudioStream:
         self._h = h
         return self
 
+    def openFromCallbacks(self, read, seek=None) -> "AudioStream":
+        """read(n) -> bytes (short = end of input), seek(position) -> None: the IOCallbacks shape of io.d:16-26."""
+        self._ensure_ctx()
+
+        def _read(buf, size, _user):
+            chunk = read(size)
+            C.memmove(buf, chunk, len(chunk))
+            return len(chunk)
+
+        def _seek(pos, _user):
+            if seek is not None:
+                seek(pos)
+            return 0
+
+        rcb, scb = READ_CB(_read), SEEK_CB(_seek)
+        h = C.c_void_p()
+        rc = self._L.l3b_stream_open_callbacks(self._ctx._h, rcb, scb, None, C.byref(h))
+        if rc:
+            raise L3BError(rc, "cannot open MP3 stream")
+        self._h = h
+        return self
+
+    def _handle(self):
+        if not self._h:
+            raise L3BError(E_PARAM, "stream is not open")
+        return self._h
+
     def close(self):
         if self._h:
             self._L.l3b_stream_close(self._h)
@@ -455,13 +541,13 @@ class AudioStream:
             pass
 
     def getNumChannels(self) -> int:
-        return self._L.l3b_stream_num_channels(self._h)
+        return self._L.l3b_stream_num_channels(self._handle())
 
     def getLengthInFrames(self) -> int:
-        return self._L.l3b_stream_length_frames(self._h)
+        return self._L.l3b_stream_length_frames(self._handle())
 
     def getSamplerate(self) -> float:
-        return self._L.l3b_stream_samplerate(self._h)
+        return self._L.l3b_stream_samplerate(self._handle())
 
     def isError(self) -> bool:
         return bool(self._L.l3b_stream_is_error(self._h))
@@ -471,16 +557,16 @@ class AudioStream:
 
     def readSamplesFloat(self, frames: int) -> np.ndarray:
         out = np.empty((frames, self.getNumChannels()), np.float32)
-        n = self._L.l3b_stream_read_float(self._h, out.ctypes.data, frames)
+        n = self._L.l3b_stream_read_float(self._handle(), out.ctypes.data, frames)
         return out[:n]
 
     def readSamplesDouble(self, frames: int) -> np.ndarray:
         out = np.empty((frames, self.getNumChannels()), np.float64)
-        n = self._L.l3b_stream_read_double(self._h, out.ctypes.data, frames)
+        n = self._L.l3b_stream_read_double(self._handle(), out.ctypes.data, frames)
         return out[:n]
 
     def seekPosition(self, frame: int) -> bool:
-        return bool(self._L.l3b_stream_seek(self._h, frame))
+        return bool(self._L.l3b_stream_seek(self._handle(), frame))
 
     def tellPosition(self) -> int:
-        return self._L.l3b_stream_tell(self._h)
+        return self._L.l3b_stream_tell(self._handle())

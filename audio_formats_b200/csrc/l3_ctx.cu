@@ -1,7 +1,9 @@
 // l3_ctx.cu -- C-ABI layer 1 ("shim"): context, batch upload/run/download.  No CPU fallback.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -32,7 +34,17 @@ struct l3b_ctx {
     int subs_of_run[kRing] = {};
     uint64_t runs = 0;
     int last_launches = 0;
+    int sms = 148;                    // multiprocessors of THIS device (grid sizing of the persistent Huffman kernels)
+    cudaEvent_t ev_wait = nullptr;    // cudaEventBlockingSync: host waits sleep instead of spinning (one core per waiting lane otherwise)
 };
+
+// Wait for everything queued on the context stream without burning a core: a pipeline keeps several lanes per GPU
+// waiting on their copies at any time, and a spinning cudaStreamSynchronize takes a host core each.
+static cudaError_t ctx_wait(l3b_ctx* c) {
+    cudaError_t e = cudaEventRecord(c->ev_wait, c->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(c->ev_wait);
+}
 
 struct l3b_resident {
     uint8_t* d_blob = nullptr;
@@ -40,7 +52,10 @@ struct l3b_resident {
     l3b_stream_desc_t* d_streams = nullptr;
     uint4* d_is = nullptr;
     uint8_t* d_sf = nullptr;
-    float* d_pcm = nullptr;
+    float* d_pcm = nullptr;                 // float PCM, or int16 PCM when flags & L3B_OUT_S16 (cap_pcm counts elements)
+    uint8_t* d_nzc = nullptr;
+    float* d_ftaps = nullptr;               // 4 x [n_grch][576] float stage snapshots (tap mode with float taps only)
+    uint32_t flags = 0;
     Tile* d_tiles[2] = {nullptr, nullptr};  // [0] stereo, [1] mono
     HuffJob* d_jobs = nullptr;              // one per granule-channel, written by the scalefactor kernel
     uint32_t* d_group_stream = nullptr;     // stream index of granule-channel 128 k, for every k (search hint)
@@ -96,6 +111,8 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** out) {
         return L3B_E_NOGPU;
     };
     if ((e = cudaSetDevice(device_id)) != cudaSuccess) return fail("cudaSetDevice", e);
+    cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device_id);
+    if ((e = cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);   // entropy launches get the higher priority: they fill idle slots
@@ -158,6 +175,7 @@ void l3b_ctx_destroy(l3b_ctx_t* c) {
     if (c->d_tables) cudaFree(c->d_tables);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
+    if (c->ev_wait) cudaEventDestroy(c->ev_wait);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     delete c;
@@ -167,7 +185,50 @@ void* l3b_ctx_cuda_stream(l3b_ctx_t* c) { return c ? (void*)c->stream : nullptr;
 
 void* l3b_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+// Page placement: cudaHostAlloc pins pages where the allocating thread's policy puts them (first touch, local node), so
+// the allocation is made by a thread that runs on the CPUs of the GPU's NUMA node for the duration of the call.
+void* l3b_host_alloc_near(int device_id, size_t bytes) {
+    cpu_set_t old_set, node_set;
+    bool moved = false;
+    char bus[32] = {0};
+    if (sched_getaffinity(0, sizeof old_set, &old_set) == 0 && cudaDeviceGetPCIBusId(bus, sizeof bus, device_id) == cudaSuccess) {
+        for (char* q = bus; *q; q++) *q = (char)tolower(*q);
+        char path[128];
+        snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+        int node = -1;
+        if (FILE* f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+        if (node >= 0) {
+            snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+            if (FILE* f = fopen(path, "r")) {
+                CPU_ZERO(&node_set);
+                int a, b2, n_set = 0;
+                char sep;
+                while (fscanf(f, "%d", &a) == 1) {
+                    b2 = a;
+                    int ch = fgetc(f);
+                    if (ch == '-') { if (fscanf(f, "%d", &b2) != 1) b2 = a; ch = fgetc(f); }
+                    for (int k = a; k <= b2 && k < CPU_SETSIZE; k++)
+                        if (CPU_ISSET(k, &old_set)) { CPU_SET(k, &node_set); n_set++; }
+                    sep = (char)ch;
+                    if (sep != ',') break;
+                }
+                fclose(f);
+                if (n_set > 0 && sched_setaffinity(0, sizeof node_set, &node_set) == 0) moved = true;
+            }
+        }
+    } else {
+        cudaGetLastError();
+    }
+    void* p = l3b_host_alloc(bytes);
+    if (p && moved) {   // touch the pages while still on the node (pinning has usually placed them already)
+        volatile uint8_t* q = static_cast<volatile uint8_t*>(p);
+        for (size_t i = 0; i < bytes; i += 4096) q[i] = 0;
+    }
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
     return p;
 }
 
@@ -184,6 +245,8 @@ void l3b_batch_free(l3b_ctx_t* c, l3b_resident_t* r) {
     cudaFree(r->d_is);
     cudaFree(r->d_sf);
     cudaFree(r->d_pcm);
+    cudaFree(r->d_nzc);
+    cudaFree(r->d_ftaps);
     cudaFree(r->d_tiles[0]);
     cudaFree(r->d_tiles[1]);
     cudaFree(r->d_jobs);
@@ -264,28 +327,41 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     if (b->maindata_bytes + 64 > r->cap_blob || b->n_grch > r->cap_grch || b->pcm_floats > r->cap_pcm ||
         b->n_streams > r->cap_streams || tiles[0].size() > r->cap_tiles[0] || tiles[1].size() > r->cap_tiles[1])
         stale = true;
-    if (stale && r->cap_blob) CU_TRY_R(cudaStreamSynchronize(c->stream));
+    const uint32_t flags = b->flags;
+    const size_t pcm_elem = (flags & L3B_OUT_S16) ? sizeof(int16_t) : sizeof(float);
+    const bool pcm_kind_changed = ((r->flags ^ flags) & L3B_OUT_S16) != 0;
+    if (pcm_kind_changed) stale = true;
+    if (stale && r->cap_blob) CU_TRY_R(ctx_wait(c));
     if (b->maindata_bytes + 64 > r->cap_blob) {
         cudaFree(r->d_blob); r->d_blob = nullptr;
         r->cap_blob = grow(b->maindata_bytes + 64);
         CU_TRY_R(cudaMalloc(&r->d_blob, r->cap_blob));
     }
     if (b->n_grch > r->cap_grch || !r->d_grch) {
-        cudaFree(r->d_grch); cudaFree(r->d_is); cudaFree(r->d_sf); cudaFree(r->d_jobs); cudaFree(r->d_group_stream);
-        r->d_grch = nullptr; r->d_is = nullptr; r->d_sf = nullptr; r->d_jobs = nullptr; r->d_group_stream = nullptr;
+        cudaFree(r->d_grch); cudaFree(r->d_is); cudaFree(r->d_sf); cudaFree(r->d_jobs); cudaFree(r->d_group_stream); cudaFree(r->d_nzc);
+        cudaFree(r->d_ftaps);
+        r->d_grch = nullptr; r->d_is = nullptr; r->d_sf = nullptr; r->d_jobs = nullptr; r->d_group_stream = nullptr; r->d_nzc = nullptr;
+        r->d_ftaps = nullptr;
         r->cap_grch = std::max<uint64_t>(1, grow(b->n_grch));
         CU_TRY_R(cudaMalloc(&r->d_grch, r->cap_grch * sizeof(l3b_grch_desc_t)));
         CU_TRY_R(cudaMalloc(&r->d_is, r->cap_grch * kIsChunks * sizeof(uint4)));
         CU_TRY_R(cudaMalloc(&r->d_sf, r->cap_grch * kSfRecBytes));
         CU_TRY_R(cudaMalloc(&r->d_jobs, r->cap_grch * sizeof(HuffJob)));
         CU_TRY_R(cudaMalloc(&r->d_group_stream, (r->cap_grch / 128 + 2) * sizeof(uint32_t)));
+        CU_TRY_R(cudaMalloc(&r->d_nzc, r->cap_grch + 16));
+    }
+    const bool want_ftaps = b->taps && (b->taps->xr || b->taps->st || b->taps->im || b->taps->dct);
+    if (want_ftaps && !r->d_ftaps) {
+        CU_TRY_R(cudaMalloc(&r->d_ftaps, r->cap_grch * 4 * 576 * sizeof(float)));
+        CU_TRY_R(cudaMemsetAsync(r->d_ftaps, 0, r->cap_grch * 4 * 576 * sizeof(float), c->stream));
     }
     if (!r->d_counters) CU_TRY_R(cudaMalloc(&r->d_counters, 2 * l3b_ctx::kMaxSubs * sizeof(uint32_t)));
-    if (b->pcm_floats > r->cap_pcm || !r->d_pcm) {
+    if (b->pcm_floats > r->cap_pcm || !r->d_pcm || pcm_kind_changed) {
         cudaFree(r->d_pcm); r->d_pcm = nullptr;
-        r->cap_pcm = std::max<uint64_t>(4, grow(b->pcm_floats));
-        CU_TRY_R(cudaMalloc(&r->d_pcm, r->cap_pcm * sizeof(float)));
+        r->cap_pcm = std::max<uint64_t>(8, grow(b->pcm_floats));
+        CU_TRY_R(cudaMalloc(&r->d_pcm, r->cap_pcm * pcm_elem));
     }
+    r->flags = flags;
     if (b->n_streams > r->cap_streams) {
         cudaFree(r->d_streams); r->d_streams = nullptr;
         r->cap_streams = (uint32_t)grow(b->n_streams);
@@ -320,7 +396,7 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
         }
     }
     CU_TRY_R(cudaMemcpyAsync(r->d_group_stream, group_stream.data(), group_stream.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY_R(cudaStreamSynchronize(c->stream));  // the host tile vectors go out of scope
+    CU_TRY_R(ctx_wait(c));  // the host tile vectors go out of scope
 #undef CU_TRY_R
     BatchParams& p = r->params;
     p.blob = r->d_blob;
@@ -330,7 +406,16 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     p.n_streams = b->n_streams;
     p.is = r->d_is;
     p.sf = r->d_sf;
-    p.pcm = r->d_pcm;
+    p.pcm = (flags & L3B_OUT_S16) ? nullptr : r->d_pcm;
+    p.pcm16 = (flags & L3B_OUT_S16) ? reinterpret_cast<int16_t*>(r->d_pcm) : nullptr;
+    p.nzc = r->d_nzc;
+    p.tap_xr = p.tap_st = p.tap_im = p.tap_dct = nullptr;
+    if (want_ftaps) {
+        p.tap_xr = r->d_ftaps;
+        p.tap_st = r->d_ftaps + r->cap_grch * 576;
+        p.tap_im = r->d_ftaps + 2 * r->cap_grch * 576;
+        p.tap_dct = r->d_ftaps + 3 * r->cap_grch * 576;
+    }
     p.jobs = r->d_jobs;
     p.group_stream = r->d_group_stream;
     p.counters = r->d_counters;
@@ -378,13 +463,14 @@ int l3b_batch_run(l3b_ctx_t* c, l3b_resident_t* r) {
         BatchParams p = r->params;
         p.grch_lo = sb.grch_lo;
         p.grch_hi = sb.grch_hi;
-        launches += launch_entropy_v4(p, i, A);
+        launches += launch_entropy_v4(p, i, c->sms, A);
         cudaEvent_t* se = ev + 3 + 3 * i;
         CU_TRY(c, cudaEventRecord(se[0], A));
         CU_TRY(c, cudaStreamWaitEvent(B, se[0], 0));   // granule kernels of sub-batch i wait for its spectra only
         CU_TRY(c, cudaEventRecord(se[1], B));
         const uint32_t n2 = sb.tile_hi[0] - sb.tile_lo[0], n1 = sb.tile_hi[1] - sb.tile_lo[1];
-        launch_granule(p, r->d_tiles[0] + sb.tile_lo[0], n2, r->d_tiles[1] + sb.tile_lo[1], n1, B, nullptr);
+        CU_TRY(c, launch_granule(p, r->d_tiles[0] + sb.tile_lo[0], n2, r->d_tiles[1] + sb.tile_lo[1], n1, B,
+                                 (r->flags & L3B_MATH_FUSED) != 0, p.tap_xr != nullptr));
         launches += (n2 > 0) + (n1 > 0);
         CU_TRY(c, cudaEventRecord(se[2], B));
     }
@@ -401,7 +487,7 @@ int l3b_batch_run(l3b_ctx_t* c, l3b_resident_t* r) {
 int l3b_batch_sync(l3b_ctx_t* c) {
     if (!c) return L3B_E_PARAM;
     CU_TRY(c, cudaSetDevice(c->device));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, ctx_wait(c));
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
@@ -432,12 +518,13 @@ int l3b_batch_timing(l3b_ctx_t* c, int last_runs, float ms[3], int* launches) {
     return 0;
 }
 
-int l3b_batch_download(l3b_ctx_t* c, l3b_resident_t* r, float* pcm_host, uint64_t first_float, uint64_t n_floats) {
-    if (!c || !r || (!pcm_host && n_floats) || first_float + n_floats > r->pcm_floats) return L3B_E_PARAM;
+int l3b_batch_download(l3b_ctx_t* c, l3b_resident_t* r, void* pcm_host, uint64_t first, uint64_t n) {
+    if (!c || !r || (!pcm_host && n) || first + n > r->pcm_floats) return L3B_E_PARAM;
     CU_TRY(c, cudaSetDevice(c->device));
-    if (n_floats)
-        CU_TRY(c, cudaMemcpyAsync(pcm_host, r->d_pcm + first_float, n_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    const size_t el = (r->flags & L3B_OUT_S16) ? sizeof(int16_t) : sizeof(float);
+    if (n)
+        CU_TRY(c, cudaMemcpyAsync(pcm_host, reinterpret_cast<const uint8_t*>(r->d_pcm) + first * el, n * el, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, ctx_wait(c));
     return 0;
 }
 
@@ -456,6 +543,12 @@ int l3b_batch_download_taps(l3b_ctx_t* c, l3b_resident_t* r, const l3b_taps_t* t
             if (taps->ist_pos) memcpy(taps->ist_pos + i * 40, rec.data() + i * kSfRecBytes + 40, 40);
         }
     }
+    float* const dst[4] = {taps->xr, taps->st, taps->im, taps->dct};
+    for (int k = 0; k < 4; k++)
+        if (dst[k] && n) {
+            if (!r->d_ftaps) { c->err = "batch was uploaded without float taps"; return L3B_E_PARAM; }
+            CU_TRY(c, cudaMemcpyAsync(dst[k], r->d_ftaps + (uint64_t)k * r->cap_grch * 576, n * 576 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        }
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;
 }

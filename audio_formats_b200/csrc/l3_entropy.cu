@@ -5,9 +5,9 @@
 // granule-channels runs as long as its slowest lane: on the 128 kbps bench streams that wastes half of all lane
 // slots.  Here the lanes of a warp are decoupled instead:
 //
-//   l3_scf_kernel       one thread per granule-channel: scalefactors (minimp3.d:613-644, 659-712) and band gains
-//                       (minimp3.d:714-719) -> 256-byte record; and a 48-byte HuffJob (bit position and window,
-//                       region books, limits) for the two kernels below
+//   l3_scf_kernel       one thread per granule-channel: scalefactors (minimp3.d:613-644, 659-712) and the granule-channel
+//                       gain 2^(gain_exp/4) (minimp3.d:714-716) -> 96-byte record; and a 48-byte HuffJob (bit position
+//                       and window, region books, limits) for the two kernels below
 //   l3_huff_big_kernel  persistent warps; every LANE pulls granule-channels from a global counter and decodes their
 //                       big_values pairs (minimp3.d:789-853), four pairs (one 16-byte chunk) per trip; a lane that
 //                       runs out of pairs parks until enough lanes are free, then they write their hand-over to
@@ -96,13 +96,14 @@ __device__ __forceinline__ float ldexp_q2(float y, int exp_q2) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Scalefactors + band gains + job setup: one thread per granule-channel
-static_assert(kSfRecBytes == 256 && sizeof(HuffJob) == 48, "the staging rows of l3_scf_kernel assume these sizes");
+static_assert(kSfRecBytes == 96 && kSfGainOff == 84 && sizeof(HuffJob) == 48, "the staging rows of l3_scf_kernel assume these sizes");
+constexpr int kRecRow = kSfRecBytes / 16 + 1;   // staging row of a record in 16-byte units (one spare: conflict-free rows)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
-    // per warp: 32 records of 17 x 16 bytes (one spare: conflict-free 16-byte rows), written out as one contiguous run
+    // per warp: 32 records of kRecRow x 16 bytes, written out as one contiguous run
     extern __shared__ __align__(16) uint4 s_stage[];
     const uint32_t lane = threadIdx.x & 31;
-    uint4* const wstage = s_stage + (threadIdx.x >> 5) * (32 * 17);
+    uint4* const wstage = s_stage + (threadIdx.x >> 5) * (32 * kRecRow);
     const uint64_t g_first = p.grch_lo + (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);   // first of this warp
     if (g_first >= p.grch_hi) return;
     const uint32_t n_live = (uint32_t)min((uint64_t)32, p.grch_hi - g_first);
@@ -120,9 +121,9 @@ __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
     br.open(d.bit_start);
 
     // ---------------- scalefactors (minimp3.d:613-644, 659-712) ----------------
-    uint32_t recw[kSfGainOff / 4];
+    uint32_t recw[kSfRecBytes / 4];
 #pragma unroll
-    for (int i = 0; i < kSfGainOff / 4; i++) recw[i] = 0;
+    for (int i = 0; i < kSfRecBytes / 4; i++) recw[i] = 0;
     uint8_t* const rec = reinterpret_cast<uint8_t*>(recw);   // thread-local staging of the record (local memory, 96 B)
     const int kind = d.kind();
     const int n_long = kind == 0 ? 22 : (kind == 1 ? 0 : (mpeg1 ? 8 : 6));
@@ -213,27 +214,17 @@ __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
         }
     }
     {
-        uint4* dst = wstage + lane * 17;   // (writing the records straight to global instead: 1.28 ms vs 1.16)
-#pragma unroll
-        for (int i = 0; i < kSfGainOff / 16; i++) dst[i] = make_uint4(recw[4 * i], recw[4 * i + 1], recw[4 * i + 2], recw[4 * i + 3]);
-        // ---------------- band gains (minimp3.d:714-719): scf[i] = 2^(gain_exp/4) * 2^(-(iscf[i] << shift)/4) ----------------
+        // ---------------- gain of the granule-channel (minimp3.d:714-716): 2^(gain_exp/4) as L3_ldexp_q2 computes it.  The 40 band
+        // gains scf[i] = gain * 2^(-(iscf[i] << shift)/4) are one more table multiplication each, done by the granule kernel.
         const bool ms_frame = (d.hdr_bits() & 0xE) == 0x6;   // HDR_IS_MS_STEREO: the 1/sqrt(2) of MS stereo is folded in here
-        const int n_sfb = kind == 0 ? 22 : (kind == 1 ? 39 : (mpeg1 ? 38 : 36));
         const int gain_exp = d.global_gain() - 4 - 210 - (ms_frame ? 2 : 0);
-        const float gain = ldexp_q2(2048.0f, 44 - gain_exp);
-        float4* gdst = reinterpret_cast<float4*>(dst + kSfGainOff / 16);
-        for (int i4 = 0; i4 < 10; i4++) {
-            float g[4];
+        recw[kSfGainOff / 4] = __float_as_uint(ldexp_q2(2048.0f, 44 - gain_exp));
+        uint4* dst = wstage + lane * kRecRow;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i = 4 * i4 + k;
-                g[k] = i < n_sfb ? ldexp_q2(gain, (int)rec[i] << scf_shift) : 0.0f;
-            }
-            gdst[i4] = make_float4(g[0], g[1], g[2], g[3]);
-        }
+        for (int i = 0; i < kSfRecBytes / 16; i++) dst[i] = make_uint4(recw[4 * i], recw[4 * i + 1], recw[4 * i + 2], recw[4 * i + 3]);
         __syncwarp();
         uint4* out = reinterpret_cast<uint4*>(p.sf + g_first * kSfRecBytes);
-        for (uint32_t idx = lane; idx < n_live * (kSfRecBytes / 16); idx += 32) out[idx] = wstage[(idx >> 4) * 17 + (idx & 15)];
+        for (uint32_t idx = lane; idx < n_live * (kSfRecBytes / 16); idx += 32) out[idx] = wstage[(idx / 6u) * kRecRow + (idx % 6u)];
         __syncwarp();
     }
 
@@ -537,6 +528,7 @@ __global__ void __launch_bounds__(128) l3_huff_c1_kernel(BatchParams p, uint32_t
     const uint4* const descs = reinterpret_cast<const uint4*>(p.grch + p.grch_lo);
     uint4* const is_base = p.is + p.grch_lo * kIsChunks;
     uint8_t* const sf_base = p.sf + p.grch_lo * kSfRecBytes;
+    uint8_t* const nzc_base = p.nzc + p.grch_lo;
 
     BitWindow bw;
     bw.words = blob32; bw.nwords = 1; bw.pos = 0; bw.w0 = bw.w1 = 0; bw.wn = bw.ready = bw.filled = 0;
@@ -560,6 +552,7 @@ __global__ void __launch_bounds__(128) l3_huff_c1_kernel(BatchParams p, uint32_t
         }
         const uint32_t chunks = (widx + 3u) >> 2;
         *reinterpret_cast<uint16_t*>(sf_base + (uint64_t)item * kSfRecBytes + 80) = (uint16_t)chunks;
+        nzc_base[item] = (uint8_t)chunks;
         if (p.zero_fill)
             for (uint32_t c = chunks; c < (uint32_t)kIsChunks; c++) is_base[(uint64_t)item * kIsChunks + c] = make_uint4(0, 0, 0, 0);
         parked = false;
@@ -624,56 +617,30 @@ __global__ void __launch_bounds__(128) l3_huff_c1_kernel(BatchParams p, uint32_t
     cp_async_wait_all();
 }
 
-void upload_entropy_constants();
+// Launch configuration of the two Huffman kernels (one variant each in the product library):
+//   lanes refill in groups of K = 16: measured (big_values / count1 ms) K=4: 4.68/2.46, 8: 4.61/2.47, 16: 4.59/2.42
+//   big_values: 8-warp CTAs share one copy of the LUT (more resident warps per SM: the kernel is latency-bound), as many
+//               CTAs per SM as fit; count1: fastest at 4 CTAs per SM (2: 3.4 ms, 4: 2.4, 6: 2.7, 10: 3.1)
+constexpr int kHuffK = 16, kBigWarps = 8, kC1CtasPerSm = 4;
 
-template <int K>
-static void launch_big(const BatchParams& p, uint32_t* cnt, uint64_t n, int sms, cudaStream_t s) {
-    constexpr int WARPS = 8;   // eight warps share one copy of the LUT: more resident warps per SM (the kernel is latency-bound)
-    static int occ = 0;
-    const size_t smem = (size_t)((p.t.huff32_entries + 3u) & ~3u) * 4 + WARPS * (96 * sizeof(uint4) + kRingWords * 32 * 4);
-    if (!occ) {
-        cudaFuncSetAttribute(l3_huff_big_kernel<K, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, l3_huff_big_kernel<K, WARPS>, 32 * WARPS, smem);
-        if (getenv("L3B_HUFF_OCC")) occ = atoi(getenv("L3B_HUFF_OCC"));
-        occ = std::max(1, occ);
-    }
-    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 32 * WARPS - 1) / (32 * WARPS), (uint64_t)sms * occ);
-    l3_huff_big_kernel<K, WARPS><<<blocks, 32 * WARPS, smem, s>>>(p, cnt);
-}
-
-int launch_entropy_v4(const BatchParams& p, int sub, cudaStream_t s) {
+int launch_entropy_v4(const BatchParams& p, int sub, int sms, cudaStream_t s) {
     if (p.grch_hi <= p.grch_lo) return 0;
-    static bool configured = false;
-    // lanes refill in groups of K: measured (big_values / count1 ms) K=4: 4.68/2.46, 8: 4.61/2.47, 16: 4.59/2.42.
-    // count1: fastest at 4 CTAs per SM (2: 3.4 ms, 4: 2.4, 6: 2.7, 10: 3.1)
-    static int k_big = 16, k_c1 = 16, occ_c1 = 4;
-    if (!configured) {
-        if (getenv("L3B_HUFF_K")) k_big = k_c1 = atoi(getenv("L3B_HUFF_K"));
-        if (getenv("L3B_HUFF_K_C1")) k_c1 = atoi(getenv("L3B_HUFF_K_C1"));
-        if (getenv("L3B_HUFF_OCC_C1")) occ_c1 = std::max(1, atoi(getenv("L3B_HUFF_OCC_C1")));
-        configured = true;
-    }
     const uint64_t n = p.grch_hi - p.grch_lo;
-    l3_scf_kernel<<<(unsigned)((n + 127) / 128), 128, 4 * 32 * 17 * sizeof(uint4), s>>>(p);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned blocks_c1 = (unsigned)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * occ_c1);
+    l3_scf_kernel<<<(unsigned)((n + 127) / 128), 128, 4 * 32 * kRecRow * sizeof(uint4), s>>>(p);
     uint32_t* cnt = p.counters + 2 * sub;
-    switch (k_big) {
-    case 1: launch_big<1>(p, cnt, n, sms, s); break;
-    case 2: launch_big<2>(p, cnt, n, sms, s); break;
-    case 4: launch_big<4>(p, cnt, n, sms, s); break;
-    case 8: launch_big<8>(p, cnt, n, sms, s); break;
-    default: launch_big<16>(p, cnt, n, sms, s); break;
+    {
+        // attribute and occupancy are per device and a process may hold contexts on several GPUs: asked every time
+        // (two cheap driver calls per launch)
+        const size_t smem = (size_t)((p.t.huff32_entries + 3u) & ~3u) * 4 + kBigWarps * (96 * sizeof(uint4) + kRingWords * 32 * 4);
+        int occ = 0;
+        cudaFuncSetAttribute(l3_huff_big_kernel<kHuffK, kBigWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, l3_huff_big_kernel<kHuffK, kBigWarps>, 32 * kBigWarps, smem);
+        occ = std::max(1, occ);
+        const unsigned blocks = (unsigned)std::min<uint64_t>((n + 32 * kBigWarps - 1) / (32 * kBigWarps), (uint64_t)sms * occ);
+        l3_huff_big_kernel<kHuffK, kBigWarps><<<blocks, 32 * kBigWarps, smem, s>>>(p, cnt);
     }
-    switch (k_c1) {
-    case 1: l3_huff_c1_kernel<1><<<blocks_c1, 128, 0, s>>>(p, cnt + 1); break;
-    case 2: l3_huff_c1_kernel<2><<<blocks_c1, 128, 0, s>>>(p, cnt + 1); break;
-    case 4: l3_huff_c1_kernel<4><<<blocks_c1, 128, 0, s>>>(p, cnt + 1); break;
-    case 8: l3_huff_c1_kernel<8><<<blocks_c1, 128, 0, s>>>(p, cnt + 1); break;
-    default: l3_huff_c1_kernel<16><<<blocks_c1, 128, 0, s>>>(p, cnt + 1); break;
-    }
+    const unsigned blocks_c1 = (unsigned)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * kC1CtasPerSm);
+    l3_huff_c1_kernel<kHuffK><<<blocks_c1, 128, 0, s>>>(p, cnt + 1);
     return 3;
 }
 

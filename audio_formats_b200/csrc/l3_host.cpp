@@ -417,18 +417,20 @@ int l3b_scan_memory(const uint8_t* data, size_t size, l3b_scan_t** out) {
 }
 
 void l3b_scan_free(l3b_scan_t* s) { delete s; }
-int l3b_scan_channels(const l3b_scan_t* s) { return s->r.channels; }
-int l3b_scan_samplerate(const l3b_scan_t* s) { return s->r.hz; }
-int l3b_scan_error(const l3b_scan_t* s) { return s->r.last_error; }
-uint64_t l3b_scan_length_frames(const l3b_scan_t* s) { return s->r.length_frames; }
-uint64_t l3b_scan_delivered_samples(const l3b_scan_t* s) { return s->r.pcm_count; }
-uint32_t l3b_scan_granules(const l3b_scan_t* s) { return s->r.prog.granules; }
-uint64_t l3b_scan_maindata_bytes(const l3b_scan_t* s) { return s->r.prog.blob.size(); }
-const uint8_t* l3b_scan_maindata(const l3b_scan_t* s) { return s->r.prog.blob.data(); }
-const l3b_grch_desc_t* l3b_scan_descs(const l3b_scan_t* s) { return s->r.prog.descs.data(); }
+int l3b_scan_channels(const l3b_scan_t* s) { return s ? s->r.channels : 0; }
+int l3b_scan_samplerate(const l3b_scan_t* s) { return s ? s->r.hz : 0; }
+int l3b_scan_error(const l3b_scan_t* s) { return s ? s->r.last_error : L3B_E_PARAM; }
+uint64_t l3b_scan_length_frames(const l3b_scan_t* s) { return s ? s->r.length_frames : 0; }
+uint64_t l3b_scan_delivered_samples(const l3b_scan_t* s) { return s ? s->r.pcm_count : 0; }
+uint32_t l3b_scan_granules(const l3b_scan_t* s) { return s ? s->r.prog.granules : 0; }
+uint64_t l3b_scan_maindata_bytes(const l3b_scan_t* s) { return s ? s->r.prog.blob.size() : 0; }
+const uint8_t* l3b_scan_maindata(const l3b_scan_t* s) { return s ? s->r.prog.blob.data() : nullptr; }
+const l3b_grch_desc_t* l3b_scan_descs(const l3b_scan_t* s) { return s ? s->r.prog.descs.data() : nullptr; }
 
 void l3b_scan_fill_stream_desc(const l3b_scan_t* s, l3b_stream_desc_t* d) {
+    if (!d) return;
     memset(d, 0, sizeof *d);
+    if (!s) return;
     d->maindata_bytes = (uint32_t)s->r.prog.blob.size();
     d->n_granules = s->r.prog.granules;
     d->pcm_skip = s->r.pcm_skip;

@@ -16,6 +16,10 @@ __constant__ float c_twid3[6];
 __constant__ float c_mdctw[36];
 __constant__ float c_sec[24];
 __constant__ float c_pan[14];
+// (1.0f, 1.0f), written at context creation.  ptxas cannot know its value, so FFMA2(a, c_one2, b) stays what it is:
+// a packed add that rounds exactly like add.rn (a * 1 is exact).  See VT<2, false>.
+__constant__ float2 c_one2;
+__constant__ float2 c_neg_one2;   // (-1, -1): the same for the packed subtraction
 
 void upload_constants() {
     cudaMemcpyToSymbol(c_expfrac, L3_EXPFRAC, sizeof c_expfrac);
@@ -25,6 +29,9 @@ void upload_constants() {
     cudaMemcpyToSymbol(c_mdctw, L3_MDCT_WINDOW, sizeof c_mdctw);
     cudaMemcpyToSymbol(c_sec, L3_SEC, sizeof c_sec);
     cudaMemcpyToSymbol(c_pan, L3_PAN, sizeof c_pan);
+    const float2 one = make_float2(1.0f, 1.0f), neg_one = make_float2(-1.0f, -1.0f);
+    cudaMemcpyToSymbol(c_one2, &one, sizeof one);
+    cudaMemcpyToSymbol(c_neg_one2, &neg_one, sizeof neg_one);
 }
 
 // =====================================================================================================
@@ -32,49 +39,48 @@ void upload_constants() {
 // =====================================================================================================
 //
 // One warp decodes a run of consecutive granules of one stream.  For stereo streams the two channels
-// travel together in every register as a float2 (T = float2): additions use the packed FADD2 of sm_100,
-// multiplications stay scalar FMULs.  (ptxas 12.9 contracts FMUL2 -> FADD2 into FFMA2 even under
-// -fmad=false; scalar multiplies feeding packed adds are left alone, which keeps every value rounded
-// exactly like the un-fused reference.)  Stage mapping inside the warp:
+// travel together in every register as a float2 (T = float2) and ALL arithmetic is packed (sm_100 FMUL2 /
+// FFMA2: one issue slot for both channels).  Stage mapping inside the warp:
 //   requant + MS stereo     lane = coefficient pair (9 per lane)
 //   antialias + IMDCT       lane = subband (overlap of the previous granule lives in registers)
 //   DCT-32                  lane = time slot (18 lanes)
 //   window                  lane = (slot parity, inner index i of minimp3.d:1371), 16-tap sliding register window
-// Shared memory per warp: spectrum T[608], DCT history T[33 rows x 33], small tables.  No block barriers.
+// Shared memory per warp: spectrum T[608], DCT history T[33 rows x 33], small tables.
+//
+// Two arithmetic modes, one source (template parameter FUSED):
+//   FUSED = false  bit-exact: every product and every sum is rounded separately, in the reference's order, so PCM is
+//                  bit-identical to the un-fused scalar reference.  ptxas 12.9 contracts a packed multiply feeding a
+//                  packed add into FFMA2 even under -fmad=false and explicit .rn, so the packed ADD is written as
+//                  FFMA2(a, ONE, b) with ONE = (1, 1) read from constant memory: a * 1 is exact, the sum is rounded
+//                  once, denormals and signed zeros behave like add.rn, and nothing is left for ptxas to contract.
+//                  Subtraction is FFMA2(b, -ONE, a).
+//   FUSED = true   tolerance mode: multiply-adds of the reference are contracted into FFMA2 by hand (one rounding
+//                  instead of two).  Not bit-identical; measured against the north star's 1e-5 FS / 99.99 % bar.
 
-#ifdef L3B_EXP_NO_PHASE_SYNC
-#define L3B_PHASE_SYNC() __syncwarp()
-#else
 #define L3B_PHASE_SYNC() __syncthreads()
-#endif
-// the three barriers of a granule (after requantisation, after the IMDCT, after the DCT) can be dropped one by one
-#ifdef L3B_EXP_NO_SYNC1
-#define L3B_PHASE_SYNC1() __syncwarp()
-#else
-#define L3B_PHASE_SYNC1() L3B_PHASE_SYNC()
-#endif
-#ifdef L3B_EXP_NO_SYNC2
-#define L3B_PHASE_SYNC2() __syncwarp()
-#else
-#define L3B_PHASE_SYNC2() L3B_PHASE_SYNC()
-#endif
-#ifndef L3B_EXP_SYNC3   // measured (config 2): without the third barrier 19.57 ms, with it 19.69; dropping the first costs
-#define L3B_PHASE_SYNC3() __syncwarp()   // 0.8 ms, the second 0.2 ms.  (A dropped CTA barrier still has to order the warp's
-                                        // own shared-memory writes before the next stage's reads: __syncwarp.)
-#else
-#define L3B_PHASE_SYNC3() L3B_PHASE_SYNC()
-#endif
 
-template <int NCH> struct VT;
-template <> struct VT<1> {
+template <int NCH, bool FUSED> struct VT;
+template <bool FUSED> struct VT<1, FUSED> {
     typedef float T;
     static __device__ __forceinline__ T zero() { return 0.0f; }
     static __device__ __forceinline__ T add(T a, T b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ T sub(T a, T b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ T mul(T a, T b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ T muls(T a, float s) { return __fmul_rn(a, s); }
     static __device__ __forceinline__ T mulw(T a, float w0, float) { return __fmul_rn(a, w0); }
     static __device__ __forceinline__ T neg(T a) { return -a; }
+    // c + a*w, c - a*w
+    static __device__ __forceinline__ T mac(T c, T a, float w) { return FUSED ? __fmaf_rn(a, w, c) : __fadd_rn(c, __fmul_rn(a, w)); }
+    static __device__ __forceinline__ T msc(T c, T a, float w) { return FUSED ? __fmaf_rn(-a, w, c) : __fsub_rn(c, __fmul_rn(a, w)); }
+    // a*wa + b*wb, a*wa - b*wb
+    static __device__ __forceinline__ T mm_add(T a, float wa, T b, float wb) {
+        return FUSED ? __fmaf_rn(b, wb, __fmul_rn(a, wa)) : __fadd_rn(__fmul_rn(a, wa), __fmul_rn(b, wb));
+    }
+    static __device__ __forceinline__ T mm_sub(T a, float wa, T b, float wb) {
+        return FUSED ? __fmaf_rn(-b, wb, __fmul_rn(a, wa)) : __fsub_rn(__fmul_rn(a, wa), __fmul_rn(b, wb));
+    }
+    // the same with one weight per channel
+    static __device__ __forceinline__ T mmw_add(T a, float wa0, float, T b, float wb0, float) { return mm_add(a, wa0, b, wb0); }
+    static __device__ __forceinline__ T mmw_sub(T a, float wa0, float, T b, float wb0, float) { return mm_sub(a, wa0, b, wb0); }
     static __device__ __forceinline__ T shfl_up(T a) { return __shfl_up_sync(0xffffffffu, a, 1); }
     static __device__ __forceinline__ T shfl_down(T a) { return __shfl_down_sync(0xffffffffu, a, 1); }
     static __device__ __forceinline__ T sel(bool c0, bool, T a, T b) { return c0 ? a : b; }
@@ -82,28 +88,39 @@ template <> struct VT<1> {
     static __device__ __forceinline__ T pack(float a, float) { return a; }
     static __device__ __forceinline__ T flip(T a, uint32_t signmask) { return __uint_as_float(__float_as_uint(a) ^ signmask); }
 };
-template <> struct VT<2> {
+template <bool FUSED> struct VT<2, FUSED> {
     typedef float2 T;
     static __device__ __forceinline__ T zero() { return make_float2(0.0f, 0.0f); }
     static __device__ __forceinline__ T neg(T a) { return make_float2(-a.x, -a.y); }
-#ifdef L3B_EXP_PACKED_MUL
-    // EXPERIMENT ONLY: packed multiplies + FADD2.FTZ (the ftz mismatch stops ptxas from contracting them into
-    // FFMA2); results below 1.18e-38 flush to zero, so this is NOT the bit-exact configuration.
-    static __device__ __forceinline__ T add(T a, T b) {
-        unsigned long long r, x = *reinterpret_cast<unsigned long long*>(&a), y = *reinterpret_cast<unsigned long long*>(&b);
-        asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
-        return *reinterpret_cast<float2*>(&r);
+    static __device__ __forceinline__ T bc(float s) { return make_float2(s, s); }
+    // a * m + c on both halves, m a 64-bit constant-bank value: kept as ONE 64-bit operand so that it lives in an
+    // aligned (uniform) register pair instead of being re-assembled from two scalars in front of every use
+    static __device__ __forceinline__ T fma_const(T a, const float2& m, T c) {
+        unsigned long long r;
+        asm("fma.rn.f32x2 %0, %1, %2, %3;"
+            : "=l"(r)
+            : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&m)),
+              "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+        return *reinterpret_cast<T*>(&r);
     }
-    static __device__ __forceinline__ T sub(T a, T b) { return add(a, neg(b)); }
-    static __device__ __forceinline__ T mul(T a, T b) { return __fmul2_rn(a, b); }
-    static __device__ __forceinline__ T muls(T a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
-#else
-    static __device__ __forceinline__ T add(T a, T b) { return __fadd2_rn(a, b); }
-    static __device__ __forceinline__ T sub(T a, T b) { return __fadd2_rn(a, neg(b)); }
-    static __device__ __forceinline__ T mul(T a, T b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
-    static __device__ __forceinline__ T muls(T a, float s) { return make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s)); }
-#endif
-    static __device__ __forceinline__ T mulw(T a, float w0, float w1) { return make_float2(__fmul_rn(a.x, w0), __fmul_rn(a.y, w1)); }
+    static __device__ __forceinline__ T add(T a, T b) { return FUSED ? __fadd2_rn(a, b) : fma_const(a, c_one2, b); }
+    static __device__ __forceinline__ T sub(T a, T b) { return FUSED ? __fadd2_rn(a, neg(b)) : fma_const(b, c_neg_one2, a); }
+    static __device__ __forceinline__ T muls(T a, float s) { return __fmul2_rn(a, bc(s)); }
+    static __device__ __forceinline__ T mulw(T a, float w0, float w1) { return __fmul2_rn(a, make_float2(w0, w1)); }
+    static __device__ __forceinline__ T mac(T c, T a, float w) { return FUSED ? __ffma2_rn(a, bc(w), c) : add(c, muls(a, w)); }
+    static __device__ __forceinline__ T msc(T c, T a, float w) { return FUSED ? __ffma2_rn(a, bc(-w), c) : sub(c, muls(a, w)); }
+    static __device__ __forceinline__ T mm_add(T a, float wa, T b, float wb) {
+        return FUSED ? __ffma2_rn(b, bc(wb), muls(a, wa)) : add(muls(a, wa), muls(b, wb));
+    }
+    static __device__ __forceinline__ T mm_sub(T a, float wa, T b, float wb) {
+        return FUSED ? __ffma2_rn(b, bc(-wb), muls(a, wa)) : sub(muls(a, wa), muls(b, wb));
+    }
+    static __device__ __forceinline__ T mmw_add(T a, float wa0, float wa1, T b, float wb0, float wb1) {
+        return FUSED ? __ffma2_rn(b, make_float2(wb0, wb1), mulw(a, wa0, wa1)) : add(mulw(a, wa0, wa1), mulw(b, wb0, wb1));
+    }
+    static __device__ __forceinline__ T mmw_sub(T a, float wa0, float wa1, T b, float wb0, float wb1) {
+        return FUSED ? __ffma2_rn(b, make_float2(-wb0, -wb1), mulw(a, wa0, wa1)) : sub(mulw(a, wa0, wa1), mulw(b, wb0, wb1));
+    }
     static __device__ __forceinline__ T shfl_up(T a) {
         return make_float2(__shfl_up_sync(0xffffffffu, a.x, 1), __shfl_up_sync(0xffffffffu, a.y, 1));
     }
@@ -147,20 +164,19 @@ __device__ __forceinline__ float requant(const float* pow43s, int v, float s) {
 }
 
 // L3_dct3_9 (minimp3.d:1022-1060), in registers
-template <int NCH>
-__device__ __forceinline__ void dct3_9(typename VT<NCH>::T* y) {
-    typedef VT<NCH> V;
+template <class V>
+__device__ __forceinline__ void dct3_9(typename V::T* y) {
     typedef typename V::T T;
     T s0, s1, s2, s3, s4, s5, s6, s7, s8, t0, t2, t4;
     s0 = y[0]; s2 = y[2]; s4 = y[4]; s6 = y[6]; s8 = y[8];
-    t0 = V::add(s0, V::muls(s6, 0.5f));
+    t0 = V::mac(s0, s6, 0.5f);
     s0 = V::sub(s0, s6);
     t4 = V::muls(V::add(s4, s2), 0.93969262f);
     t2 = V::muls(V::add(s8, s2), 0.76604444f);
     s6 = V::muls(V::sub(s4, s8), 0.17364818f);
     s4 = V::add(s4, V::sub(s8, s2));
 
-    s2 = V::sub(s0, V::muls(s4, 0.5f));
+    s2 = V::msc(s0, s4, 0.5f);
     y[4] = V::add(s4, s0);
     s8 = V::add(V::sub(t0, t2), s6);
     s0 = V::add(V::sub(t0, t4), t2);
@@ -189,10 +205,8 @@ __device__ __forceinline__ void dct3_9(typename VT<NCH>::T* y) {
 }
 
 // L3_imdct36 for one band (minimp3.d:1062-1100).  ws0/ws1: window row (0 normal, 1 stop) per channel.
-template <int NCH>
-__device__ __forceinline__ void imdct36_band(const typename VT<NCH>::T* x, typename VT<NCH>::T* ovl, int ws0, int ws1,
-                                             typename VT<NCH>::T* out) {
-    typedef VT<NCH> V;
+template <class V>
+__device__ __forceinline__ void imdct36_band(const typename V::T* x, typename V::T* ovl, int ws0, int ws1, typename V::T* out) {
     typedef typename V::T T;
     T co[9], si[9];
     co[0] = V::neg(x[0]);
@@ -204,8 +218,8 @@ __device__ __forceinline__ void imdct36_band(const typename VT<NCH>::T* x, typen
         si[7 - 2 * i] = V::sub(x[4 * i + 4], x[4 * i + 3]);
         co[2 + 2 * i] = V::neg(V::add(x[4 * i + 3], x[4 * i + 4]));
     }
-    dct3_9<NCH>(co);
-    dct3_9<NCH>(si);
+    dct3_9<V>(co);
+    dct3_9<V>(si);
     si[1] = V::neg(si[1]);
     si[3] = V::neg(si[3]);
     si[5] = V::neg(si[5]);
@@ -215,56 +229,57 @@ __device__ __forceinline__ void imdct36_band(const typename VT<NCH>::T* x, typen
 #pragma unroll
     for (int i = 0; i < 9; i++) {
         T o = ovl[i];
-        T sum = V::add(V::muls(co[i], c_twid9[9 + i]), V::muls(si[i], c_twid9[0 + i]));
-        ovl[i] = V::sub(V::muls(co[i], c_twid9[0 + i]), V::muls(si[i], c_twid9[9 + i]));
-        out[i] = V::sub(V::mulw(o, wa[0 + i], wb[0 + i]), V::mulw(sum, wa[9 + i], wb[9 + i]));
-        out[17 - i] = V::add(V::mulw(o, wa[9 + i], wb[9 + i]), V::mulw(sum, wa[0 + i], wb[0 + i]));
+        T sum = V::mm_add(co[i], c_twid9[9 + i], si[i], c_twid9[0 + i]);
+        ovl[i] = V::mm_sub(co[i], c_twid9[0 + i], si[i], c_twid9[9 + i]);
+        out[i] = V::mmw_sub(o, wa[0 + i], wb[0 + i], sum, wa[9 + i], wb[9 + i]);
+        out[17 - i] = V::mmw_add(o, wa[9 + i], wb[9 + i], sum, wa[0 + i], wb[0 + i]);
     }
 }
 
 // L3_idct3 / L3_imdct12 (minimp3.d:1102-1129); X(k) = x[OFF + 3k]
-template <int NCH, int OFF>
-__device__ __forceinline__ void imdct12(const typename VT<NCH>::T* x, typename VT<NCH>::T* dst, typename VT<NCH>::T* overlap) {
-    typedef VT<NCH> V;
+template <class V, int OFF>
+__device__ __forceinline__ void imdct12(const typename V::T* x, typename V::T* dst, typename V::T* overlap) {
     typedef typename V::T T;
     T co[3], si[3];
     {
         T x0 = V::neg(x[OFF + 0]), x1 = V::add(x[OFF + 6], x[OFF + 3]), x2 = V::add(x[OFF + 12], x[OFF + 9]);
-        T m1 = V::muls(x1, 0.86602540f), a1 = V::sub(x0, V::muls(x2, 0.5f));
-        co[1] = V::add(x0, x2); co[0] = V::add(a1, m1); co[2] = V::sub(a1, m1);
+        T a1 = V::msc(x0, x2, 0.5f);
+        co[1] = V::add(x0, x2); co[0] = V::mac(a1, x1, 0.86602540f); co[2] = V::msc(a1, x1, 0.86602540f);
     }
     {
         T x0 = x[OFF + 15], x1 = V::sub(x[OFF + 12], x[OFF + 9]), x2 = V::sub(x[OFF + 6], x[OFF + 3]);
-        T m1 = V::muls(x1, 0.86602540f), a1 = V::sub(x0, V::muls(x2, 0.5f));
-        si[1] = V::add(x0, x2); si[0] = V::add(a1, m1); si[2] = V::sub(a1, m1);
+        T a1 = V::msc(x0, x2, 0.5f);
+        si[1] = V::add(x0, x2); si[0] = V::mac(a1, x1, 0.86602540f); si[2] = V::msc(a1, x1, 0.86602540f);
     }
     si[1] = V::neg(si[1]);
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         T o = overlap[i];
-        T sum = V::add(V::muls(co[i], c_twid3[3 + i]), V::muls(si[i], c_twid3[0 + i]));
-        overlap[i] = V::sub(V::muls(co[i], c_twid3[0 + i]), V::muls(si[i], c_twid3[3 + i]));
-        dst[i] = V::sub(V::muls(o, c_twid3[2 - i]), V::muls(sum, c_twid3[5 - i]));
-        dst[5 - i] = V::add(V::muls(o, c_twid3[5 - i]), V::muls(sum, c_twid3[2 - i]));
+        T sum = V::mm_add(co[i], c_twid3[3 + i], si[i], c_twid3[0 + i]);
+        overlap[i] = V::mm_sub(co[i], c_twid3[0 + i], si[i], c_twid3[3 + i]);
+        dst[i] = V::mm_sub(o, c_twid3[2 - i], sum, c_twid3[5 - i]);
+        dst[5 - i] = V::mm_add(o, c_twid3[5 - i], sum, c_twid3[2 - i]);
     }
 }
 
 // L3_imdct_short for one band (minimp3.d:1131-1142)
-template <int NCH>
-__device__ __forceinline__ void imdct_short_band(const typename VT<NCH>::T* x, typename VT<NCH>::T* ovl, typename VT<NCH>::T* out) {
-    typedef typename VT<NCH>::T T;
+template <class V>
+__device__ __forceinline__ void imdct_short_band(const typename V::T* x, typename V::T* ovl, typename V::T* out) {
+    typedef typename V::T T;
 #pragma unroll
     for (int i = 0; i < 6; i++) out[i] = ovl[i];
-    imdct12<NCH, 0>(x, out + 6, ovl + 6);
-    imdct12<NCH, 1>(x, out + 12, ovl + 6);
+    imdct12<V, 0>(x, out + 6, ovl + 6);
+    imdct12<V, 1>(x, out + 12, ovl + 6);
     T nd[6];
-    imdct12<NCH, 2>(x, nd, ovl + 6);
+    imdct12<V, 2>(x, nd, ovl + 6);
 #pragma unroll
     for (int i = 0; i < 6; i++) ovl[i] = nd[i];
 }
 
 constexpr int kDStride = 33;  // T elements per row (odd: the DCT's per-slot column writes hit distinct banks)
-constexpr int kMaxIter = kTileGranules + 2;
+// a tile's own granules + the recompute halo: two granules, three when the halo would otherwise start on the second
+// granule of an intensity-stereo frame (whose intensity positions are per-FRAME scratch, see below)
+constexpr int kMaxIter = kTileGranules + 3;
 
 // ---- mbarrier + TMA (1-D bulk copy) helpers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -301,12 +316,12 @@ struct __align__(16) WarpSmem {
     // DCT-32 outputs, 33 rows x 33: rows 0..14 are the history (qmf_state), rows 15..32 belong to the current
     // granule.  The current-granule rows ALIAS the spectrum buffer `xr` (natural layout while requantising,
     // x19 padded layout between IMDCT and DCT): each stage has consumed its input before the next one writes.
-    typename VT<NCH>::T Dbuf[1 + 15 * kDStride + kXrStride];  // D = Dbuf + 1, so that row 15 (= xr) is 16-byte aligned
-#ifndef L3B_EXP_DIRECT_IS
-    uint4 st_is[NCH * kIsChunks];              // TMA-staged inputs of the next granule: quantised spectra,
-#endif
+    typename VT<NCH, false>::T Dbuf[1 + 15 * kDStride + kXrStride];  // D = Dbuf + 1, so that row 15 (= xr) is 16-byte aligned
+    uint4 st_is[NCH * kIsChunks];              // TMA-staged inputs of the next granule: quantised spectra (only the chunks
+                                               //   that hold anything: `nz_chunks` of each channel),
     uint4 st_rec[NCH * kSfRecBytes / 16];      //   scalefactor records,
     uint4 st_desc[NCH];                        //   descriptors
+    float gains[NCH][40];                      // band gains of this granule (minimp3.d:714-719)
     uint8_t sfbpair[3][288];
     uint8_t ist[40];
     uint8_t smode[40];
@@ -315,7 +330,9 @@ struct __align__(16) WarpSmem {
 };
 
 // The (rare) band where the two channels of a granule use different transforms: one channel at a time.
+template <bool FUSED>
 __device__ __noinline__ void imdct_split(float2* x, float2* ovl, float2* y, bool sh0, bool sh1, int ws0, int ws1) {
+    typedef VT<1, FUSED> V1;
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         float xs[18], os[9], ys[18];
@@ -323,8 +340,8 @@ __device__ __noinline__ void imdct_split(float2* x, float2* ovl, float2* y, bool
         for (int i = 0; i < 18; i++) xs[i] = c ? x[i].y : x[i].x;
 #pragma unroll
         for (int i = 0; i < 9; i++) os[i] = c ? ovl[i].y : ovl[i].x;
-        if (c ? sh1 : sh0) imdct_short_band<1>(xs, os, ys);
-        else imdct36_band<1>(xs, os, c ? ws1 : ws0, 0, ys);
+        if (c ? sh1 : sh0) imdct_short_band<V1>(xs, os, ys);
+        else imdct36_band<V1>(xs, os, c ? ws1 : ws0, 0, ys);
 #pragma unroll
         for (int i = 0; i < 18; i++) { if (c) y[i].y = ys[i]; else y[i].x = ys[i]; }
 #pragma unroll
@@ -332,22 +349,25 @@ __device__ __noinline__ void imdct_split(float2* x, float2* ovl, float2* y, bool
     }
 }
 // mono: the same out-of-line route for the one rare case it has (a per-lane window row, see below)
+template <bool FUSED>
 __device__ __noinline__ void imdct_split(float* x, float* ovl, float* y, bool sh0, bool, int ws0, int) {
-    if (sh0) imdct_short_band<1>(x, ovl, y);
-    else imdct36_band<1>(x, ovl, ws0, 0, y);
+    typedef VT<1, FUSED> V1;
+    if (sh0) imdct_short_band<V1>(x, ovl, y);
+    else imdct36_band<V1>(x, ovl, ws0, 0, y);
 }
 
-#ifndef L3B_GRANULE_WARPS_PER_SM
-#define L3B_GRANULE_WARPS_PER_SM 16
-#endif
-template <int NCH, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
-    typedef VT<NCH> V;
+constexpr int kCtaTableBytes = 1040 + 496 + 2048;   // s_pow43 (257 floats + pad) | s_ldexp (121 floats + pad) | s_win (16 x 32 floats)
+
+template <int NCH, int WARPS, bool FUSED, bool TAPS>
+__global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
+    typedef VT<NCH, FUSED> V;
     typedef typename V::T T;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    float* s_pow43 = reinterpret_cast<float*>(smem_raw);  // 257 signed entries (+pad), shared by the CTA
+    float* s_pow43 = reinterpret_cast<float*>(smem_raw);          // 257 signed entries (+pad), shared by the CTA
+    float* s_ldexp = reinterpret_cast<float*>(smem_raw + 1040);   // one step of L3_ldexp_q2: g_expfrac[e & 3] * 2^(30 - (e >> 2)), e <= 120
+    float* s_win = reinterpret_cast<float*>(smem_raw + 1040 + 496);   // synthesis window weights per lane: [tap k][w0 / w1][lane]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem<NCH>& W = *reinterpret_cast<WarpSmem<NCH>*>(smem_raw + 1040 + (size_t)warp * sizeof(WarpSmem<NCH>));
+    WarpSmem<NCH>& W = *reinterpret_cast<WarpSmem<NCH>*>(smem_raw + kCtaTableBytes + (size_t)warp * sizeof(WarpSmem<NCH>));
     T* const D = W.Dbuf + 1;
     T* const xr = D + 15 * kDStride;
 
@@ -355,6 +375,8 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
         const float pw = p.t.pow43[i < 128 ? 128 - i : i - 128];
         s_pow43[i] = i < 128 ? -pw : pw;
     }
+    for (int i = threadIdx.x; i <= 120; i += 32 * WARPS)
+        s_ldexp[i] = __fmul_rn(c_expfrac[i & 3], __int_as_float((127 + 30 - (i >> 2)) << 23));   // both factors exact: (float)((1 << 30) >> (i >> 2))
 
     const uint32_t tile_idx = blockIdx.x * WARPS + warp;
     const bool have_tile = tile_idx < n_tiles;
@@ -366,15 +388,15 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
     for (int i = lane; i < 3 * 288 / 4; i += 32)
         reinterpret_cast<uint32_t*>(&W.sfbpair[0][0])[i] = reinterpret_cast<const uint32_t*>(p.t.sfb_of_pair + row * 3 * 288)[i];
     for (int i = lane; i < 15 * kDStride; i += 32) D[i] = V::zero();
+    for (int i = lane; i < 40; i += 32) W.ist[i] = 0;
     if (lane == 0) mbar_init(&W.mbar, 1);
 
-    // synthesis window weights of this lane: inner index ii = lane & 15 (0..14 active), slot parity par
+    // synthesis window weights of a lane: inner index ii = lane & 15 (0..14 active), slot parity par.  Kept in shared memory
+    // and fetched at the start of every window stage: held in registers across the IMDCT they cost 16 registers there.
     const int ii = lane & 15, par = lane >> 4;
-    float w0[8], w1[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        w0[k] = ii < 15 ? __ldg(p.t.win + (k * 2 + 0) * 15 + ii) : 0.0f;
-        w1[k] = ii < 15 ? __ldg(p.t.win + (k * 2 + 1) * 15 + ii) : 0.0f;
+    for (int i = threadIdx.x; i < 16 * 32; i += 32 * WARPS) {
+        const int l = i & 31, kc = i >> 5;
+        s_win[i] = (l & 15) < 15 ? __ldg(p.t.win + kc * 15 + (l & 15)) : 0.0f;
     }
 
     // recompute halo: up to two granules before the tile, unless decoder state was zeroed in between
@@ -383,6 +405,14 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
         const l3b_grch_desc_t* dp = p.grch + S.first_grch + (uint64_t)start * NCH;
         if (__ldg(&dp->w3) >> 31) break;
         start--;
+    }
+    // The intensity positions of a frame are per-FRAME scratch in the reference (minimp3.d:1497): what granule 1 does not
+    // transmit keeps what granule 0 left there.  A halo that starts on granule 1 of an intensity-stereo frame therefore
+    // starts one granule earlier, so that granule 0's intensity pass has run (it only matters when the two channels use
+    // different block types, but the extra granule is cheap: it happens once per tile of a stream with an odd delay).
+    if (NCH == 2 && have_tile && start > 0 && start < (int)tile.g0) {
+        const Desc ds = load_desc(p.grch + S.first_grch + (uint64_t)start * NCH);
+        if (ds.second_granule() && !ds.reset_before() && (ds.hdr_bits() & 1)) start--;
     }
     const int n_iter = have_tile ? (int)(tile.g0 + tile.ng) - start : 0;
     T ovl[9];
@@ -393,47 +423,43 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
 
     const int n_long_bands_mixed = 2 << (row == 1 ? 1 : 0);  // minimp3.d:1218
     const uint64_t skipf = S.pcm_skip / NCH, countf = S.pcm_count / NCH;   // in frames
-    T* const pcm = reinterpret_cast<T*>(p.pcm + S.pcm_off);
-#ifdef L3B_EXP_DIRECT_IS
-    constexpr uint32_t kStageBytes = NCH * (kSfRecBytes + 16);   // experiment: spectra are read straight from global memory
-#else
-    constexpr uint32_t kStageBytes = NCH * (kIsChunks * 16 + kSfRecBytes + 16);
-#endif
+    // delivery: float samples, or 16-bit ones at the same element offsets (one pointer, element size by flag)
+    const bool out16 = p.pcm16 != nullptr;
+    char* const out_base = out16 ? reinterpret_cast<char*>(p.pcm16 + S.pcm_off) : reinterpret_cast<char*>(p.pcm + S.pcm_off);
 
-    auto prefetch = [&](int g) {  // lane 0: TMA bulk copies of granule g's inputs into the staging buffers
+    // lane 0: TMA bulk copies of granule g's inputs into the staging buffers.  Only the chunks of the spectra that
+    // hold anything are fetched: n0 / n1 = nz_chunks of the two channels (from p.nzc, read a granule ahead).
+    auto prefetch = [&](int g, uint32_t n0, uint32_t n1) {
         const uint64_t di = S.first_grch + (uint64_t)g * NCH;
-        mbar_expect_tx(&W.mbar, kStageBytes);
-#ifndef L3B_EXP_DIRECT_IS
-        tma_load_1d(W.st_is, p.is + di * kIsChunks, NCH * kIsChunks * 16, &W.mbar);
-#endif
+        mbar_expect_tx(&W.mbar, (n0 + n1) * 16u + NCH * (kSfRecBytes + 16));
+        if (n0) tma_load_1d(W.st_is, p.is + di * kIsChunks, n0 * 16u, &W.mbar);
+        if (NCH == 2 && n1) tma_load_1d(W.st_is + kIsChunks, p.is + (di + 1) * kIsChunks, n1 * 16u, &W.mbar);
         tma_load_1d(W.st_rec, p.sf + di * kSfRecBytes, NCH * kSfRecBytes, &W.mbar);
         tma_load_1d(W.st_desc, p.grch + di, NCH * 16, &W.mbar);
     };
-    if (lane == 0 && n_iter > 0) prefetch(start);
+    auto load_nz = [&](int g, uint32_t& n0, uint32_t& n1) {
+        const uint8_t* q = p.nzc + S.first_grch + (uint64_t)g * NCH;
+        n0 = __ldg(q);
+        n1 = NCH == 2 ? __ldg(q + 1) : 0u;
+    };
+    uint32_t nzn0 = 0, nzn1 = 0;   // lane 0: nz_chunks of the NEXT granule
+    if (lane == 0 && n_iter > 0) {
+        load_nz(start, nzn0, nzn1);
+        prefetch(start, nzn0, nzn1);
+    }
 
     for (int it = 0; it < kMaxIter; it++) {
         const bool act = it < n_iter;
         const int g = start + it;
         const int mode = g >= (int)tile.g0 ? 2 : (g == (int)tile.g0 - 1 ? 1 : 0);
+        const uint64_t di = S.first_grch + (uint64_t)g * NCH;
         Desc d0, d1;
         d0.bit_start = d0.w1 = d0.w2 = d0.w3 = 0;
         d1 = d0;
         int kind0 = 0, kind1 = 0, hb = 0;
         bool ms_frame = false, istereo = false;
-#ifdef L3B_EXP_DIRECT_IS
-        uint32_t gva[9], gvb[9];
-        const uint32_t* const gis = reinterpret_cast<const uint32_t*>(p.is + (S.first_grch + (uint64_t)g * NCH) * kIsChunks);
         if (act) {
-#pragma unroll
-            for (int m = 0; m < 9; m++) {
-                gva[m] = __ldg(gis + lane + 32 * m);
-                gvb[m] = NCH == 2 ? __ldg(gis + kIsChunks * 4 + lane + 32 * m) : 0u;
-            }
-            if (it + 1 < n_iter && lane < NCH * 9)   // next granule's rows into L2: 9 lines of 128 bytes per channel
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(gis) + NCH * kIsChunks * 16 + lane * 128));
-        }
-#endif
-        if (act) {
+            if (lane == 0 && it + 1 < n_iter) load_nz(g + 1, nzn0, nzn1);   // used after requantisation
             mbar_wait(&W.mbar, it & 1);
             {
                 const uint4 v = W.st_desc[0];
@@ -453,9 +479,26 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
             const uint8_t* rec0 = reinterpret_cast<const uint8_t*>(W.st_rec);
             const uint8_t* rec1 = rec0 + (NCH - 1) * kSfRecBytes;
 
-            // band gains (minimp3.d:714-719) come ready-made in the scalefactor record (l3_scf_kernel)
-            const float* const scf0 = reinterpret_cast<const float*>(rec0 + kSfGainOff);
-            const float* const scf1 = reinterpret_cast<const float*>(rec1 + kSfGainOff);
+            // band gains (minimp3.d:714-719): scf[i] = gain * 2^(-(iscf[i] << shift)/4); `gain` = 2^(gain_exp/4) comes with
+            // the record (l3_scf_kernel), the per-band factor is one table step of L3_ldexp_q2 (two or more when the
+            // exponent exceeds 120, which takes a scalefactor above 30).
+            for (int i = lane; i < NCH * 40; i += 32) {
+                const int c = (NCH == 2 && i >= 40) ? 1 : 0, b = i - 40 * c;
+                const uint8_t* rc = c ? rec1 : rec0;
+                const Desc& dc = c ? d1 : d0;
+                const int kd = c ? kind1 : kind0;
+                const int n_sfb = kd == 0 ? 22 : (kd == 1 ? 39 : (mpeg1 ? 38 : 36));
+                float y = *reinterpret_cast<const float*>(rc + kSfGainOff);
+                int e = (int)rc[b] << (dc.scalefac_scale() + 1);
+                do {
+                    const int k = e < 120 ? e : 120;
+                    y = __fmul_rn(y, s_ldexp[k]);
+                    e -= k;
+                } while (e > 0);
+                W.gains[c][b] = b < n_sfb ? y : 0.0f;
+            }
+            const float* const scf0 = W.gains[0];
+            const float* const scf1 = W.gains[NCH - 1];
             if (istereo) {
                 // ist_pos is per-FRAME scratch in the reference (zeroed at frame start, minimp3.d:1497): what granule 1 of
                 // channel 1 does not transmit keeps granule 0's values, including the top-band entries that granule 0's
@@ -467,15 +510,10 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
             __syncwarp();
 
             // ---------------- requantisation (minimp3.d:813-816, 846, 874-878) + MS stereo (:885-896) -------
-#ifndef L3B_EXP_SKIP_REQUANT
             {
                 const int nch0 = *reinterpret_cast<const uint16_t*>(rec0 + 80);
                 const int nch1 = *reinterpret_cast<const uint16_t*>(rec1 + 80);
-#ifdef L3B_EXP_DIRECT_IS
-                const uint32_t* isw0 = gis;
-#else
                 const uint32_t* isw0 = reinterpret_cast<const uint32_t*>(W.st_is);
-#endif
                 const uint32_t* isw1 = isw0 + (NCH - 1) * (kIsChunks * 4);
                 const bool ms_now = NCH == 2 && ms_frame && !istereo;
                 const int nz_hi = max(nch0, NCH == 2 ? nch1 : 0);   // chunks (8 coefficients) holding anything non-zero
@@ -493,15 +531,12 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                     if (8 * m >= nz_hi) {   // warp-uniform: both channels are zero from here on (+0.0, like the memset grbuf)
                         if (NCH == 2) *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                         else *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(0.0f, 0.0f);
+                        if (TAPS && mode == 2)
+                            for (int c = 0; c < NCH; c++) p.tap_xr[(di + c) * 576 + 2 * pi] = p.tap_xr[(di + c) * 576 + 2 * pi + 1] = 0.0f;
                         continue;
                     }
-#ifdef L3B_EXP_DIRECT_IS
-                    const uint32_t va = (pi >> 2) < nch0 ? gva[m] : 0u;
-                    const uint32_t vb = (NCH == 2 && (pi >> 2) < nch1) ? gvb[m] : 0u;
-#else
-                    const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;   // chunks past nz_chunks were never written
+                    const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;   // chunks past nz_chunks were never fetched
                     const uint32_t vb = (NCH == 2 && (pi >> 2) < nch1) ? isw1[pi] : 0u;
-#endif
                     const float sa = scf0[W.sfbpair[kind0][pi]];
                     const float sb = NCH == 2 ? scf1[W.sfbpair[kind1][pi]] : 0.0f;
                     // a 16-bit value lies in [-128, 127] iff its bits 15..7 are all equal
@@ -512,6 +547,10 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                     if (NCH == 2) {
                         float b0 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((((int)(vb << 16) >> 14) & 0x3FC) ^ 0x200)), sb);
                         float b1 = __fmul_rn(*reinterpret_cast<const float*>(tab + (((((int)vb >> 16) << 2) & 0x3FC) ^ 0x200)), sb);
+                        if (TAPS && mode == 2) {
+                            p.tap_xr[di * 576 + 2 * pi] = a0; p.tap_xr[di * 576 + 2 * pi + 1] = a1;
+                            p.tap_xr[(di + 1) * 576 + 2 * pi] = b0; p.tap_xr[(di + 1) * 576 + 2 * pi + 1] = b1;
+                        }
                         if (ms_now) {
                             const float l0 = __fadd_rn(a0, b0), r0 = __fsub_rn(a0, b0);
                             const float l1 = __fadd_rn(a1, b1), r1 = __fsub_rn(a1, b1);
@@ -519,6 +558,7 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                         }
                         *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(a0, b0, a1, b1);
                     } else {
+                        if (TAPS && mode == 2) { p.tap_xr[di * 576 + 2 * pi] = a0; p.tap_xr[di * 576 + 2 * pi + 1] = a1; }
                         *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(a0, a1);
                     }
                 }
@@ -536,6 +576,10 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                             const float sb = scf1[W.sfbpair[kind1][pi]];
                             float b0 = requant(s_pow43, (int)(int16_t)(vb & 0xFFFFu), sb);
                             float b1 = requant(s_pow43, (int)(int16_t)(vb >> 16), sb);
+                            if (TAPS && mode == 2) {
+                                p.tap_xr[di * 576 + 2 * pi] = a0; p.tap_xr[di * 576 + 2 * pi + 1] = a1;
+                                p.tap_xr[(di + 1) * 576 + 2 * pi] = b0; p.tap_xr[(di + 1) * 576 + 2 * pi + 1] = b1;
+                            }
                             if (ms_now) {
                                 const float l0 = __fadd_rn(a0, b0), r0 = __fsub_rn(a0, b0);
                                 const float l1 = __fadd_rn(a1, b1), r1 = __fsub_rn(a1, b1);
@@ -543,17 +587,17 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                             }
                             *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(a0, b0, a1, b1);
                         } else {
+                            if (TAPS && mode == 2) { p.tap_xr[di * 576 + 2 * pi] = a0; p.tap_xr[di * 576 + 2 * pi + 1] = a1; }
                             *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(a0, a1);
                         }
                     }
                 }
             }
-#endif
             __syncwarp();
             // the staging buffers are free again: fetch the next granule while this one is transformed
             if (lane == 0 && it + 1 < n_iter) {
-                fence_proxy_async();   // measured free (19.64 ms with or without); kept for the generic -> async proxy ordering
-                prefetch(g + 1);
+                fence_proxy_async();   // generic -> async proxy ordering of the staging buffers
+                prefetch(g + 1, nzn0, nzn1);
             }
 
             // ---------------- intensity stereo (minimp3.d:898-982), on channel 0's band layout ----------------
@@ -635,11 +679,16 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                 for (int m = 0; m < 18; m++) X[lane + 32 * m] = __fmul_rn(X[lane + 32 * m], k);
                 __syncwarp();
             }
+            if (TAPS && mode == 2) {   // spectrum after stereo processing (after minimp3.d:1213)
+                for (int m = 0; m < 18; m++) {
+                    const int k = lane + 32 * m;
+                    for (int c = 0; c < NCH; c++) p.tap_st[(di + c) * 576 + k] = V::ch(xr[k], c);
+                }
+            }
         }
-        L3B_PHASE_SYNC1();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
+        L3B_PHASE_SYNC();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
 
         // ---------------- reorder + antialias + IMDCT + frequency inversion (minimp3.d:1215-1229) ----------
-#ifndef L3B_EXP_SKIP_IMDCT
         if (act) {
             T x[18], y[18];
             const int bt0 = d0.block_type(), bt1 = d1.block_type();
@@ -674,8 +723,8 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                 for (int i = 0; i < 8; i++) {
                     const T dn = V::shfl_up(x[17 - i]);   // band-1, element 17-i
                     const T up = V::shfl_down(x[i]);      // band+1, element i
-                    nlo[i] = V::sub(V::muls(x[i], c_aa[i]), V::muls(dn, c_aa[8 + i]));
-                    nhi[i] = V::add(V::muls(up, c_aa[8 + i]), V::muls(x[17 - i], c_aa[i]));
+                    nlo[i] = V::mm_sub(x[i], c_aa[i], dn, c_aa[8 + i]);
+                    nhi[i] = V::mm_add(up, c_aa[8 + i], x[17 - i], c_aa[i]);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
@@ -687,12 +736,11 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
             // window row: the stop window, except in the long bands of a granule whose mixed_block_flag is set --
             // the reference honours the flag on every block type (minimp3.d:1212, 1158-1167), so a STOP block that
             // closes a mixed run keeps the normal window in its lowest bands.  Only then does the row differ from lane to
-            // lane; everywhere else it is warp-uniform, and the window weights stay uniform constant-bank operands
-            // (19.64 -> 19.53 ms; an all-uniform build measured 19.35).
+            // lane; everywhere else it is warp-uniform, and the window weights stay uniform constant-bank operands.
             const bool stop_mixed = (bt0 == 3 && d0.mixed()) || (NCH == 2 && bt1 == 3 && d1.mixed());
             if (!stop_mixed && (NCH == 1 || sh0 == sh1)) {
-                if (sh0) imdct_short_band<NCH>(x, ovl, y);
-                else imdct36_band<NCH>(x, ovl, bt0 == 3 ? 1 : 0, bt1 == 3 ? 1 : 0, y);
+                if (sh0) imdct_short_band<V>(x, ovl, y);
+                else imdct36_band<V>(x, ovl, bt0 == 3 ? 1 : 0, bt1 == 3 ? 1 : 0, y);
             } else {
                 // Rare: the channels use different transforms in this band, or the window row is per lane.  The
                 // out-of-line helper works on COPIES so that x / ovl / y themselves never have their address taken
@@ -704,7 +752,7 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                 for (int i = 0; i < 18; i++) xc[i] = x[i];
 #pragma unroll
                 for (int i = 0; i < 9; i++) oc[i] = ovl[i];
-                imdct_split(xc, oc, yc, sh0, sh1, ws0, ws1);
+                imdct_split<FUSED>(xc, oc, yc, sh0, sh1, ws0, ws1);
 #pragma unroll
                 for (int i = 0; i < 18; i++) y[i] = yc[i];
 #pragma unroll
@@ -716,13 +764,15 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                 for (int i = 1; i < 18; i += 2) y[i] = V::flip(y[i], fm);
 #pragma unroll
                 for (int i = 0; i < 18; i++) xr[lane * 19 + i] = y[i];
+                if (TAPS && mode == 2) {
+                    for (int i = 0; i < 18; i++)
+                        for (int c = 0; c < NCH; c++) p.tap_im[(di + c) * 576 + lane * 18 + i] = V::ch(y[i], c);
+                }
             }
         }
-#endif
-        L3B_PHASE_SYNC2();
+        L3B_PHASE_SYNC();
 
         // ---------------- DCT-32 matrixing across bands, one time slot per lane (minimp3.d:1232-1298) -------
-#ifndef L3B_EXP_SKIP_DCT
         if (act && mode >= 1 && lane < 18) {
             T t[4][8];
 #pragma unroll
@@ -756,9 +806,9 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                 x6 = V::muls(V::add(x6, x7), 0.70710677f);
                 x7 = V::add(x7, xt);
                 x3 = V::muls(V::add(x3, x4), 0.70710677f);
-                x5 = V::sub(x5, V::muls(x7, 0.198912367f));
-                x7 = V::add(x7, V::muls(x5, 0.382683432f));
-                x5 = V::sub(x5, V::muls(x7, 0.198912367f));
+                x5 = V::msc(x5, x7, 0.198912367f);
+                x7 = V::mac(x7, x5, 0.382683432f);
+                x5 = V::msc(x5, x7, 0.198912367f);
                 x0 = V::sub(xt, x6); xt = V::add(xt, x6);
                 t[r][1] = V::muls(V::add(xt, x7), 0.50979561f);
                 t[r][2] = V::muls(V::add(x4, x3), 0.54119611f);
@@ -779,12 +829,15 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
             out[29] = V::add(t[2][7], t[3][7]);
             out[30] = t[1][7];
             out[31] = t[3][7];
+            if (TAPS && mode == 2) {   // the reference's in-place layout: output j of slot k at grbuf[j*18 + k]
+                __syncwarp(0x3FFFFu);
+                for (int j = 0; j < 32; j++)
+                    for (int c = 0; c < NCH; c++) p.tap_dct[(di + c) * 576 + j * 18 + lane] = V::ch(out[j], c);
+            }
         }
-#endif
-        L3B_PHASE_SYNC3();
+        __syncwarp();   // (a CTA barrier here measured slower; the warp's own writes must still be ordered before the window's reads)
 
         // ---------------- 512-tap window (minimp3.d:1305-1406) ----------------
-#ifndef L3B_EXP_SKIP_WINDOW
         if (act && mode == 2) {
             const uint64_t f0 = (uint64_t)g * 576u;   // first frame of this granule in the decoded signal
             // samples [lo, hi) of this granule are delivered (all 576 except at the edges of the stream's PCM range)
@@ -793,9 +846,34 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
             const int dhi = (int)max(0ll, min(576ll, rel + (long long)countf));
             const unsigned span = (unsigned)(dhi - dlo);
 #define L3B_DELIVER(f) ((unsigned)((f) - dlo) < span)
-            T* const out = pcm + (f0 - skipf);        // only dereferenced for delivered frames
+            // frame index in the delivered signal of this granule's first frame (pointers only dereferenced for delivered frames)
+            const long long obase = (long long)f0 - (long long)skipf;
+            T* const out = reinterpret_cast<T*>(out_base) + obase;
+            int16_t* const out16p = reinterpret_cast<int16_t*>(out_base) + obase * NCH;
             const float scale = 1.0f / 32768.0f;
+            // 16-bit delivery: q = clamp(lrintf(x * 32768), -32768, 32767) of the float sample x the float path would
+            // have written (the conversion SURVEY 8c defines; un-dithered, wav.d:475-700)
+            auto store = [&](int f, T v) {
+                const T s = V::muls(v, scale);
+                if (out16) {
+                    if (NCH == 2) {
+                        const int q0 = max(-32768, min(32767, __float2int_rn(__fmul_rn(V::ch(s, 0), 32768.0f))));
+                        const int q1 = max(-32768, min(32767, __float2int_rn(__fmul_rn(V::ch(s, 1), 32768.0f))));
+                        reinterpret_cast<uint32_t*>(out16p)[f] = (uint32_t)(q0 & 0xFFFF) | ((uint32_t)q1 << 16);
+                    } else {
+                        out16p[f] = (int16_t)max(-32768, min(32767, __float2int_rn(__fmul_rn(V::ch(s, 0), 32768.0f))));
+                    }
+                } else {
+                    out[f] = s;
+                }
+            };
             if (ii < 15) {
+                float w0[8], w1[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    w0[k] = s_win[(2 * k) * 32 + lane];
+                    w1[k] = s_win[(2 * k + 1) * 32 + lane];
+                }
                 // lane (par, ii) produces samples 15-ii and 17+ii of slots s = 2q + par.
                 // V[j] = D[row par + j][ j odd ? 31-ii : 1+ii ]  -- row r of D is slot r-15 ("window")
                 // Sliding window of 16 taps in registers; three slots per loop trip (the window then moves by 6
@@ -818,20 +896,26 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                         T a, b;
                         {
                             const T vz = Vw[2 * qq + 15], vy = Vw[2 * qq + 0];
-                            b = V::add(V::muls(vz, w1[0]), V::muls(vy, w0[0]));
-                            a = V::sub(V::muls(vz, w0[0]), V::muls(vy, w1[0]));
+                            b = V::mm_add(vz, w1[0], vy, w0[0]);
+                            a = V::mm_sub(vz, w0[0], vy, w1[0]);
                         }
 #pragma unroll
                         for (int k = 1; k < 8; k++) {
                             const T vz = Vw[2 * qq + 15 - k], vy = Vw[2 * qq + k];
-                            b = V::add(b, V::add(V::muls(vz, w1[k]), V::muls(vy, w0[k])));
-                            if (k & 1) a = V::add(a, V::sub(V::muls(vy, w1[k]), V::muls(vz, w0[k])));
-                            else a = V::add(a, V::sub(V::muls(vz, w0[k]), V::muls(vy, w1[k])));
+                            if (FUSED) {
+                                b = V::mac(V::mac(b, vz, w1[k]), vy, w0[k]);
+                                if (k & 1) a = V::msc(V::mac(a, vy, w1[k]), vz, w0[k]);
+                                else a = V::msc(V::mac(a, vz, w0[k]), vy, w1[k]);
+                            } else {
+                                b = V::add(b, V::mm_add(vz, w1[k], vy, w0[k]));
+                                if (k & 1) a = V::add(a, V::mm_sub(vy, w1[k], vz, w0[k]));
+                                else a = V::add(a, V::mm_sub(vz, w0[k], vy, w1[k]));
+                            }
                         }
                         const int s = 2 * (3 * q3 + qq) + par;
                         const int fa = 32 * s + 15 - ii, fb = 32 * s + 17 + ii;
-                        if (L3B_DELIVER(fa)) out[fa] = V::muls(a, scale);
-                        if (L3B_DELIVER(fb)) out[fb] = V::muls(b, scale);
+                        if (L3B_DELIVER(fa)) store(fa, a);
+                        if (L3B_DELIVER(fb)) store(fb, b);
                     }
 #pragma unroll
                     for (int j = 0; j < 16; j++) Vw[j] = Vw[j + 6];   // slide by three slots
@@ -845,29 +929,28 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
                 for (int k = 0; k < 15; k++) z[k] = col[k * kDStride + 16];
                 T a;
                 a = V::muls(V::sub(z[14], z[0]), 29.0f);
-                a = V::add(a, V::muls(V::add(z[1], z[13]), 213.0f));
-                a = V::add(a, V::muls(V::sub(z[12], z[2]), 459.0f));
-                a = V::add(a, V::muls(V::add(z[3], z[11]), 2037.0f));
-                a = V::add(a, V::muls(V::sub(z[10], z[4]), 5153.0f));
-                a = V::add(a, V::muls(V::add(z[5], z[9]), 6574.0f));
-                a = V::add(a, V::muls(V::sub(z[8], z[6]), 37489.0f));
-                a = V::add(a, V::muls(z[7], 75038.0f));
+                a = V::mac(a, V::add(z[1], z[13]), 213.0f);
+                a = V::mac(a, V::sub(z[12], z[2]), 459.0f);
+                a = V::mac(a, V::add(z[3], z[11]), 2037.0f);
+                a = V::mac(a, V::sub(z[10], z[4]), 5153.0f);
+                a = V::mac(a, V::add(z[5], z[9]), 6574.0f);
+                a = V::mac(a, V::sub(z[8], z[6]), 37489.0f);
+                a = V::mac(a, z[7], 75038.0f);
                 const int fa = 32 * lane, fb = 32 * lane + 16;
-                if (L3B_DELIVER(fa)) out[fa] = V::muls(a, scale);
+                if (L3B_DELIVER(fa)) store(fa, a);
 #pragma unroll
                 for (int k = 0; k < 15; k += 2) z[k] = col[k * kDStride];
                 a = V::muls(z[14], 104.0f);
-                a = V::add(a, V::muls(z[12], 1567.0f));
-                a = V::add(a, V::muls(z[10], 9727.0f));
-                a = V::add(a, V::muls(z[8], 64019.0f));
-                a = V::add(a, V::muls(z[6], -9975.0f));
-                a = V::add(a, V::muls(z[4], -45.0f));
-                a = V::add(a, V::muls(z[2], 146.0f));
-                a = V::add(a, V::muls(z[0], -5.0f));
-                if (L3B_DELIVER(fb)) out[fb] = V::muls(a, scale);
+                a = V::mac(a, z[12], 1567.0f);
+                a = V::mac(a, z[10], 9727.0f);
+                a = V::mac(a, z[8], 64019.0f);
+                a = V::mac(a, z[6], -9975.0f);
+                a = V::mac(a, z[4], -45.0f);
+                a = V::mac(a, z[2], 146.0f);
+                a = V::mac(a, z[0], -5.0f);
+                if (L3B_DELIVER(fb)) store(fb, a);
             }
         }
-#endif
 #undef L3B_DELIVER
         // slide the history: the last 15 slots become rows 0..14 (qmf_state, minimp3.d:1423-1433)
         if (act && mode >= 1) {
@@ -910,28 +993,31 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_GRANULE_WARPS_PER_SM / WARPS) 
     }
 }
 
-template <int NCH, int WARPS>
-static void launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n, cudaStream_t s) {
-    if (!n) return;
-    static bool configured = false;
-    static const size_t pad = getenv("L3B_GRANULE_SMEM_PAD") ? (size_t)atoi(getenv("L3B_GRANULE_SMEM_PAD")) : 0;   // occupancy experiments
-    const size_t smem = 1040 + (size_t)WARPS * sizeof(WarpSmem<NCH>) + pad;
-    if (!configured) {
-        cudaFuncSetAttribute(l3_granule_kernel<NCH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
-    l3_granule_kernel<NCH, WARPS><<<(n + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(p, tiles, n);
+template <int NCH, int WARPS, bool FUSED, bool TAPS>
+static cudaError_t launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    const size_t smem = kCtaTableBytes + (size_t)WARPS * sizeof(WarpSmem<NCH>);
+    // the attribute is per device and a process may hold contexts on several: set it every time (a cheap driver call)
+    cudaError_t e = cudaFuncSetAttribute(l3_granule_kernel<NCH, WARPS, FUSED, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    l3_granule_kernel<NCH, WARPS, FUSED, TAPS><<<(n + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(p, tiles, n);
+    return cudaGetLastError();
 }
 
-void launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
-                    uint32_t n_mono, cudaStream_t s, cudaEvent_t ev_mid) {
-    static const int warps_env = getenv("L3B_GRANULE_WARPS") ? atoi(getenv("L3B_GRANULE_WARPS")) : kGranuleWarpsStereo;
-    if (warps_env == 8) launch_granule_t<2, 8>(p, tiles_stereo, n_stereo, s);
-    else if (warps_env == 16) launch_granule_t<2, 16>(p, tiles_stereo, n_stereo, s);
-    else if (warps_env == 2) launch_granule_t<2, 2>(p, tiles_stereo, n_stereo, s);
-    else launch_granule_t<2, kGranuleWarpsStereo>(p, tiles_stereo, n_stereo, s);
-    if (ev_mid) cudaEventRecord(ev_mid, s);
-    launch_granule_t<1, kGranuleWarpsMono>(p, tiles_mono, n_mono, s);
+cudaError_t launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
+                           uint32_t n_mono, cudaStream_t s, bool fused, bool taps) {
+    cudaError_t e;
+    if (taps) {   // float taps exist in the bit-exact mode only (they are compared bitwise)
+        e = launch_granule_t<2, kGranuleWarpsStereo, false, true>(p, tiles_stereo, n_stereo, s);
+        if (e == cudaSuccess) e = launch_granule_t<1, kGranuleWarpsMono, false, true>(p, tiles_mono, n_mono, s);
+    } else if (fused) {
+        e = launch_granule_t<2, kGranuleWarpsStereo, true, false>(p, tiles_stereo, n_stereo, s);
+        if (e == cudaSuccess) e = launch_granule_t<1, kGranuleWarpsMono, true, false>(p, tiles_mono, n_mono, s);
+    } else {
+        e = launch_granule_t<2, kGranuleWarpsStereo, false, false>(p, tiles_stereo, n_stereo, s);
+        if (e == cudaSuccess) e = launch_granule_t<1, kGranuleWarpsMono, false, false>(p, tiles_mono, n_mono, s);
+    }
+    return e;
 }
 
 }  // namespace l3b

@@ -22,8 +22,9 @@
 
 namespace l3b {
 
-constexpr int kSfRecBytes = 256;   // per granule-channel: iscf[40] ist_pos[40] nz_chunks(u16) pad[14] gains f32[40]
-constexpr int kSfGainOff = 96;     // byte offset of the 40 band gains (minimp3.d:714-719) inside the record
+constexpr int kSfRecBytes = 96;    // per granule-channel: iscf[40] ist_pos[40] nz_chunks(u16) pad[2] gain(f32) pad[8]
+constexpr int kSfGainOff = 84;     // byte offset of the granule-channel gain 2^(gain_exp/4) (minimp3.d:714-716) inside the record;
+                                   // the 40 band gains are one table multiplication each in the granule kernel
 constexpr int kIsChunks = 72;      // 576 int16 = 72 x 16 bytes
 #ifndef L3B_TILE_GRANULES
 #define L3B_TILE_GRANULES 64
@@ -75,8 +76,11 @@ struct BatchParams {
     const l3b_stream_desc_t* streams;
     uint32_t n_streams;
     uint4* is;       // [n_grch][72] packed int16x8
-    uint8_t* sf;     // [n_grch][96]
-    float* pcm;
+    uint8_t* sf;     // [n_grch][kSfRecBytes]
+    uint8_t* nzc;    // [n_grch] nz_chunks again, packed: read a granule ahead by the granule kernel to size its TMA copies
+    float* pcm;      // float delivery (NULL when pcm16 is set)
+    int16_t* pcm16;  // 16-bit delivery: q = clamp(lrintf(x * 32768)) of the float sample, same element offsets
+    float *tap_xr, *tap_st, *tap_im, *tap_dct;   // [n_grch][576] float stage snapshots (test taps; TAPS kernels only)
     uint64_t grch_lo, grch_hi;  // granule-channel range the entropy kernels cover in this launch
     int zero_fill;   // the count1 kernel zero-fills the chunks it does not reach (tap mode)
     HuffJob* jobs;        // [n_grch]
@@ -88,13 +92,14 @@ struct BatchParams {
 constexpr int kGranuleWarpsStereo = 4;   // warps (= tiles) per CTA of the granule kernel; 16 warps resident per SM.
 constexpr int kGranuleWarpsMono = 4;     // 4-warp CTAs measured best (16: 33.7 ms, 8: 28.6 ms, 4: 27.2 ms on config 2)
 
-template <int NCH, int WARPS>
+template <int NCH, int WARPS, bool FUSED, bool TAPS>
 __global__ void l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles);
 
 // lane-decoupled entropy path: scalefactor kernel, big_values kernel, count1 kernel (l3_entropy.cu); returns launches
-int launch_entropy_v4(const BatchParams& p, int sub, cudaStream_t s);
-void launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
-                    uint32_t n_mono, cudaStream_t s, cudaEvent_t ev_mid);
+int launch_entropy_v4(const BatchParams& p, int sub, int sms, cudaStream_t s);
+// fused: tolerance-mode arithmetic (hand-contracted FFMA2) instead of the bit-exact one; taps: float stage snapshots
+cudaError_t launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
+                           uint32_t n_mono, cudaStream_t s, bool fused, bool taps);
 void upload_constants();
 void upload_entropy_constants();
 

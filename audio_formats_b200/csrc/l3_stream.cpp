@@ -15,7 +15,10 @@
 using namespace l3b;
 
 namespace {
-constexpr int kDecodeAheadFrames = 64;  // frames walked (and decoded in one launch) per refill
+// Frames walked (and decoded in one batch) per refill.  Large on purpose: a refill costs one upload, four launches and one
+// download whatever its size, and 64 frames are two warps' worth of work on a 148-SM part.  2,048 frames are 53 s of
+// 44.1 kHz audio (19 MB of float stereo PCM in the cache): the transcode loop of a typical file is one or two refills.
+constexpr int kDecodeAheadFrames = 2048;
 }
 
 struct l3b_stream {
@@ -152,6 +155,11 @@ static long stream_read_samples(l3b_stream* s, float* buf, size_t samples) {
             if (s->input_ended) break;
             int rc = refill(s);
             if (rc) {
+                // Sticky, like a decode error of the reference (minimp3_ex.d:796): the frames just walked have no PCM
+                // behind them, so they must not be consumed by a later read.  A seek restarts the run and clears it.
+                s->look.clear();
+                s->input_ended = true;
+                s->last_error = rc;
                 s->error = true;
                 s->err = std::string("GPU decode failed: ") + l3b_last_error(s->ctx);
                 return rc;
@@ -335,12 +343,33 @@ int l3b_stream_open_file(l3b_ctx_t* ctx, const char* path, l3b_stream_t** out) {
     }
 }
 
+// mp3dec_io_t-shaped open (minimp3_ex.d:61-71, mp3dec_ex_open_cb :929; thunks stream.d:2243-2254): the GPU path decodes
+// ahead in large windows and seeks freely, so the callbacks are drained into memory once, here, instead of by the caller.
+int l3b_stream_open_callbacks(l3b_ctx_t* ctx, l3b_read_cb read, l3b_seek_cb seek, void* user, l3b_stream_t** out) {
+    if (!read || !out) return L3B_E_PARAM;
+    try {
+        if (seek && seek(0, user) != 0) return L3B_E_IOERROR;
+        std::vector<uint8_t> bytes;
+        for (;;) {
+            const size_t at = bytes.size();
+            bytes.resize(at + kIoSize);
+            const size_t got = read(bytes.data() + at, kIoSize, user);
+            if (got > kIoSize) return L3B_E_IOERROR;
+            bytes.resize(at + got);
+            if (got != kIoSize) break;   // short read = end of input (minimp3_ex.d:831-836)
+        }
+        return stream_open(ctx, std::move(bytes), out);
+    } catch (const std::bad_alloc&) {
+        return L3B_E_MEMORY;
+    }
+}
+
 void l3b_stream_close(l3b_stream_t* s) { delete s; }
-int l3b_stream_num_channels(const l3b_stream_t* s) { return s->channels; }
-int64_t l3b_stream_length_frames(const l3b_stream_t* s) { return s->length_frames; }
-float l3b_stream_samplerate(const l3b_stream_t* s) { return (float)s->hz; }
-int l3b_stream_is_error(const l3b_stream_t* s) { return s->error ? 1 : 0; }
-const char* l3b_stream_error_message(const l3b_stream_t* s) { return s->err.c_str(); }
+int l3b_stream_num_channels(const l3b_stream_t* s) { return s ? s->channels : 0; }
+int64_t l3b_stream_length_frames(const l3b_stream_t* s) { return s ? s->length_frames : 0; }
+float l3b_stream_samplerate(const l3b_stream_t* s) { return s ? (float)s->hz : 0.0f; }
+int l3b_stream_is_error(const l3b_stream_t* s) { return (!s || s->error) ? 1 : 0; }   // a stream starts errored (stream.d:1379)
+const char* l3b_stream_error_message(const l3b_stream_t* s) { return s ? s->err.c_str() : "stream is not open"; }
 
 // stream.d:537-551
 int l3b_stream_read_float(l3b_stream_t* s, float* out, int frames) {
@@ -375,6 +404,6 @@ int l3b_stream_seek(l3b_stream_t* s, int frame) {
 }
 
 // stream.d:1214-1218
-int l3b_stream_tell(const l3b_stream_t* s) { return (int)s->cur_sample / s->channels; }
+int l3b_stream_tell(const l3b_stream_t* s) { return (s && s->channels) ? (int)(s->cur_sample / (uint64_t)s->channels) : 0; }
 
 }  // extern "C"

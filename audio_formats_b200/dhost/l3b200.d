@@ -47,7 +47,14 @@ struct l3b_taps_t
     short* is_;
     ubyte* iscf;
     ubyte* ist_pos;
+    float* xr;
+    float* st;
+    float* im;
+    float* dct;
 }
+
+enum L3B_OUT_S16 = 1;          // 16-bit delivery: clamp(lrintf(x * 32768)), the un-dithered conversion of wav.d:475-700
+enum L3B_MATH_FUSED = 2;    // tolerance-mode arithmetic (FMA-contracted), not bit-identical
 
 struct l3b_batch_t
 {
@@ -57,16 +64,42 @@ struct l3b_batch_t
     ulong n_grch;
     const(l3b_stream_desc_t)* streams;
     uint n_streams;
-    float* pcm;
+    void* pcm;               // float* or short* (L3B_OUT_S16)
     ulong pcm_floats;
     int* status;
     const(l3b_taps_t)* taps;
+    uint flags;
+    uint reserved;
 }
+
+struct l3b_pipeline_opts_t
+{
+    int lanes;
+    int wave_streams;
+    int scan_threads;
+    uint flags;
+}
+
+struct l3b_stream_result_t
+{
+    ulong pcm_off;
+    ulong frames;
+    int channels;
+    int samplerate;
+    int status;
+    int device;
+}
+
+enum L3B_PIPELINE_PHASES = 6;
+alias l3b_read_cb = size_t function(void* buf, size_t size, void* user);   // mp3dec_io_t.read, minimp3_ex.d:61-71
+alias l3b_seek_cb = int function(ulong position, void* user);              // mp3dec_io_t.seek
 
 struct l3b_ctx;
 struct l3b_resident;
 struct l3b_scan;
 struct l3b_stream;
+struct l3b_pipeline;
+alias l3b_pipeline_t = l3b_pipeline;
 alias l3b_ctx_t = l3b_ctx;
 alias l3b_resident_t = l3b_resident;
 alias l3b_scan_t = l3b_scan;
@@ -78,6 +111,7 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** outCtx);
 void l3b_ctx_destroy(l3b_ctx_t* ctx);
 const(char)* l3b_last_error(const(l3b_ctx_t)* ctx);
 void* l3b_host_alloc(size_t bytes);
+void* l3b_host_alloc_near(int device_id, size_t bytes);
 void l3b_host_free(void* p);
 int l3b_decode_batch(l3b_ctx_t* ctx, const(l3b_batch_t)* batch);
 int l3b_batch_upload(l3b_ctx_t* ctx, const(l3b_batch_t)* batch, l3b_resident_t** outResident);
@@ -85,7 +119,7 @@ int l3b_batch_upload_reuse(l3b_ctx_t* ctx, const(l3b_batch_t)* batch, l3b_reside
 int l3b_batch_reupload(l3b_ctx_t* ctx, l3b_resident_t* r, const(l3b_batch_t)* batch);
 int l3b_batch_run(l3b_ctx_t* ctx, l3b_resident_t* r);
 int l3b_batch_sync(l3b_ctx_t* ctx);
-int l3b_batch_download(l3b_ctx_t* ctx, l3b_resident_t* r, float* pcm_host, ulong first_float, ulong n_floats);
+int l3b_batch_download(l3b_ctx_t* ctx, l3b_resident_t* r, void* pcm_host, ulong first, ulong n);
 int l3b_batch_download_taps(l3b_ctx_t* ctx, l3b_resident_t* r, const(l3b_taps_t)* taps);
 void* l3b_batch_device_pcm(l3b_resident_t* r);
 void l3b_batch_free(l3b_ctx_t* ctx, l3b_resident_t* r);
@@ -110,6 +144,14 @@ int l3b_scans_assemble(l3b_scan_t** scans, uint n, ubyte* blob, ulong blobCap, l
                        l3b_stream_desc_t* streams, l3b_batch_t* batch);
 int l3b_decode_scans(l3b_ctx_t* ctx, l3b_scan_t** scans, uint n, float** pcm, int* status);
 
+int l3b_pipeline_create(const(int)* device_ids, int n_devices, const(l3b_pipeline_opts_t)* opts, l3b_pipeline_t** outPipeline);
+void l3b_pipeline_destroy(l3b_pipeline_t* p);
+int l3b_pipeline_decode(l3b_pipeline_t* p, const(ubyte*)* data, const(size_t)* size, uint n, void* outPcm, ulong outCapacity,
+                        l3b_stream_result_t* results, ulong* outUsed);
+int l3b_pipeline_profile(l3b_pipeline_t* p, double* seconds6);
+const(char)* l3b_pipeline_last_error(const(l3b_pipeline_t)* p);
+
+int l3b_stream_open_callbacks(l3b_ctx_t* ctx, l3b_read_cb read, l3b_seek_cb seek, void* user, l3b_stream_t** outStream);
 int l3b_stream_open_memory(l3b_ctx_t* ctx, const(ubyte)* data, size_t size, l3b_stream_t** outStream);
 int l3b_stream_open_file(l3b_ctx_t* ctx, const(char)* path, l3b_stream_t** outStream);
 void l3b_stream_close(l3b_stream_t* s);

@@ -7,13 +7,19 @@
 A "step" is one pass of the hot path over one batch of synthetic streams.  At N=1 the workload is
 BASELINE.json configs[1]: 1,024 synthetic 60 s 44.1 kHz stereo 128 kbps MPEG-1 Layer III long-block
 streams (seeds 0..1023).  N>1: streams shard by file, 1,024 streams per GPU, no collective (weak scaling).
+`--workload config3|config4|config5` runs the other BASELINE configurations at their stated sizes (config5: 65,536
+logical 180 s 320 kbps streams over U unique payloads, in device-resident waves, sharded over the ranks: strong scaling).
 
-`value`   device-resident throughput: bitstreams + descriptors already in HBM; one step = scalefactor kernel +
-          big_values kernel + count1 kernel (integer, "entropy") + fused granule kernel (float).
-`e2e`     MP3 bytes in host memory -> float PCM in pinned host memory through the public batch API:
-          host prepass (frame sync / side info / reservoir slicing, all host threads) + H2D + kernels + D2H.
-`roofline` of the dominant (granule) kernel; `cpu_baseline`: the C oracle (port of the D reference, which
-          cannot be built here: no D compiler) on the host cores, timed in the same run.
+`value`    device-resident throughput of the bit-exact path: bitstreams + descriptors already in HBM; one step =
+           scalefactor kernel + big_values kernel + count1 kernel (integer, "entropy") + fused granule kernel (float).
+`e2e`      MP3 bytes in host memory -> 16-bit PCM in pinned host memory through the library's batch pipeline
+           (l3b_pipeline_decode): host prepass + H2D + kernels + D2H, all inside the timed region.  `e2e.f32` is the same
+           with float delivery.  The reference arm converts to 16 bit too (the transcode example writes 16-bit WAV).
+`roofline` of the dominant (granule) kernel against the SLOWER of the FP32 and HBM roofs, bit-exact mode, plus the
+           tolerance-mode (FMA-contracted) kernel and its measured deviation; `cpu_baseline`: the C oracle (port of the D
+           reference, which cannot be built here: no D compiler) on the host cores, timed in the same run;
+`parity`   the measured batch checked in this run: a seeded sample of streams bit-exact against the oracle, and every
+           stream's checksum against a second decode (the pipeline's, which tiles and batches them differently).
 """
 from __future__ import annotations
 
@@ -24,6 +30,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
@@ -34,12 +41,13 @@ import numpy as np  # noqa: E402
 
 METRIC = "mp3_batch_decode_audio_seconds_per_second"
 UNIT = "audio-s/s"
-FLOPS_PER_GRCH = 32734          # SURVEY.md 8d / BASELINE.md 3: float add/sub/mul per granule-channel
+FLOPS_PER_GRCH = 32734          # SURVEY.md 8d / BASELINE.md 3: float add/sub/mul per granule-channel of the reference
 FP32_NOMINAL_TFLOPS = 74.45     # 148 SM x 128 lanes x 2 x 1.965 GHz (not measured by the driver)
 # tools/microbench/fp32_pipes.cu on this pool's B200: FMUL / FADD / FADD2 / FMUL2 all retire ~125 lane-ops per clock per SM
 # (3.8 scalar or 1.95 packed warp-instructions): the FP32 pipe does 148 x 125 x 1.965e9 = 36.4e12 un-fused flop/s
 FP32_UNFUSED_MEASURED_TFLOPS = 36.4
 HBM_FALLBACK_GBS = 6650.0       # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+TRAFFIC_FILE = "r02_traffic.json"
 
 
 def host_threads() -> int:
@@ -63,6 +71,10 @@ def gen_streams(seeds, seconds, threads):
 
     with ThreadPoolExecutor(threads) as ex:
         return list(ex.map(one, seeds))
+
+
+def q16(x):
+    return np.clip(np.rint(x.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -115,20 +127,26 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_decode_throughput(streams, threads, min_seconds=0.0):
-    """Decode `streams` with the oracle's transcode loop on `threads` host threads; returns (audio_s, wall_s)."""
+def cpu_decode_throughput(streams, threads, s16=True):
+    """Decode `streams` with the oracle's transcode loop (1,024-frame reads; every chunk converted to 16 bit when s16)
+    on `threads` host threads; returns (audio_s, wall_s)."""
     import oracle
     oracle.build()
     oracle.lib()
 
     def one(st):
-        n, nch, hz, _ = oracle.transcode_loop(st.data, 1024, keep=False)
+        n, nch, hz, _ = oracle.transcode_loop(st.data, 1024, keep=False, s16=s16)
         return n / hz
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
         audio = sum(ex.map(one, streams))
     return audio, time.perf_counter() - t0
+
+
+def cpu_baseline_note():
+    return "C restatement of the reference's D decoder (no D compiler in this image), transcode loop with 1,024-frame reads, " \
+           "each chunk converted to 16 bit like the reference's WAV writer (un-dithered)"
 
 
 def run_reference(args, rank, world):
@@ -151,26 +169,103 @@ def run_reference(args, rank, world):
         audio += a; wall += w
     value = audio / wall
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": workload_scaling(), "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": workload_config(args, n_sample, "bounded sample of the same seeded streams"),
+            "config": workload_config(args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{n_sample} streams x {args.seconds:g} s per step, transcode loop (1024-frame reads)",
-                             "note": "C restatement of the reference's D decoder; the D build itself could not be produced here"},
+                             "sample": f"{n_sample} streams x {args.seconds:g} s per step (a bounded sample of the same seeded streams)",
+                             "note": cpu_baseline_note()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, n_streams, note=""):
-    if WORKLOAD != "config2":
-        return {"workload": f"side measurement, generator profile {WORKLOAD}: {n_streams} streams x {args.seconds:g} s per GPU",
-                "streams_per_gpu": n_streams, "seconds_per_stream": args.seconds, "sharding": "by file, no collective",
-                "l2": "inputs larger than L2 (no flush needed)", **({"note": note} if note else {})}
-    return {"workload": f"BASELINE.json configs[1]: {n_streams} synthetic {args.seconds:g} s 44.1 kHz stereo 128 kbps "
-                        f"MPEG-1 Layer III long-block streams per GPU (seeds rank*streams+i)",
-            "streams_per_gpu": n_streams, "seconds_per_stream": args.seconds, "sharding": "by file, no collective",
-            "l2": "inputs larger than L2 (no flush needed)", **({"note": note} if note else {})}
+def workload_scaling():
+    return "strong" if WORKLOAD == "config5" else "weak"
+
+
+def workload_config(args):
+    """Identical in both arms (the driver compares the dicts)."""
+    n, sec = args.streams, args.seconds
+    names = {
+        "config2": f"BASELINE.json configs[1]: {n} synthetic {sec:g} s 44.1 kHz stereo 128 kbps MPEG-1 Layer III long-block "
+                   f"streams per GPU (seeds rank*streams+i)",
+        "config3": f"BASELINE.json configs[2]: {n} synthetic {sec:g} s 44.1 kHz 128 kbps streams per GPU with mixed long/short/mixed "
+                   f"blocks, joint (MS + intensity) stereo, heavy bit-reservoir use",
+        "config4": f"BASELINE.json configs[3]: heterogeneous batch of {n} streams x {sec:g} s per GPU mixing 32/44.1/48 kHz MPEG-1 and "
+                   f"16/22.05/24 kHz MPEG-2 LSF, 64-320 kbps, mono and stereo",
+        "config5": f"BASELINE.json configs[4]: {args.logical} logical 44.1 kHz stereo 320 kbps streams x {sec:g} s over "
+                   f"{args.unique} unique payloads, file-sharded over the GPUs, device-resident waves of {args.wave} streams",
+    }
+    return {"workload": names[WORKLOAD], "streams_per_gpu": n, "seconds_per_stream": sec,
+            "sharding": "by file, no collective", "l2": "inputs larger than L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------------------------------------
+class Join:
+    """Barrier + max/sum over ranks.  The data path has no collective (streams are independent), so the only thing the
+    ranks exchange is timing scalars: a gloo group on the host does it; NCCL is not used anywhere."""
+
+    def __init__(self, world):
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("gloo")
+            self.dist = dist
+
+    def barrier(self):
+        import torch
+        torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+
+    def _red(self, x, op):
+        if not self.dist:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX) if self.dist else x
+
+    def sum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM) if self.dist else x
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def d2h_rate_gbs(torch, join, gib=1, reps=3):
+    """Device -> pinned host copy rate of this box: 1 GiB, best of 3, all ranks AT THE SAME TIME between two barriers
+    (per-rank rate and the aggregate): the ceiling of any end-to-end number that delivers PCM to the host."""
+    try:
+        n = gib << 28
+        src = torch.empty(n, dtype=torch.float32, device="cuda")
+        dst = torch.empty(n, dtype=torch.float32).pin_memory()
+        best = 0.0
+        for _ in range(reps):
+            join.barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(); dst.copy_(src, non_blocking=True); c1.record(); torch.cuda.synchronize()
+            ms = join.max(c0.elapsed_time(c1))     # the slowest rank of a concurrent round
+            best = max(best, (n * 4) / (ms * 1e-3) / 1e9)
+        del src, dst
+        return best
+    except RuntimeError:   # a side measurement must not take the bench down
+        return None
+
+
+def stream_crcs(buf: np.ndarray, spans, threads):
+    """crc32 of every stream's PCM bytes in `buf` (spans: (element offset, element count))."""
+    def one(sp):
+        o, n = sp
+        return zlib.crc32(buf[o:o + n].data)
+
+    with ThreadPoolExecutor(threads) as ex:
+        return list(ex.map(one, spans))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -180,20 +275,30 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
-    ap.add_argument("--seconds", type=float, default=60.0, help="seconds per stream")
+    ap.add_argument("--streams", type=int, default=None, help="streams per GPU (default: the configuration's size)")
+    ap.add_argument("--seconds", type=float, default=None, help="seconds per stream (default: the configuration's)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-lanes", type=int, default=6)
+    ap.add_argument("--e2e-lanes", type=int, default=4)
     ap.add_argument("--e2e-wave", type=int, default=16, help="streams per pipeline wave")
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="skip the tolerance-mode kernel measurement")
+    ap.add_argument("--parity-sample", type=int, default=16, help="streams compared bit-exactly with the oracle in this run")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
-                    help="config2 is the metric configuration; the others are side measurements of the parity-test shapes")
+                    help="config2 is the metric configuration; config3/4/5 are the other BASELINE configurations at full size")
+    ap.add_argument("--logical", type=int, default=65536, help="config5: logical streams of the whole job")
+    ap.add_argument("--unique", type=int, default=64, help="config5: unique payloads (device-resident, shared by the logical streams)")
+    ap.add_argument("--wave", type=int, default=1024, help="config5: logical streams per device-resident wave")
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload
+    defaults = {"config2": (1024, 60.0), "config3": (1024, 60.0), "config4": (4096, 30.0), "config5": (0, 180.0)}[WORKLOAD]
+    if args.streams is None:
+        args.streams = defaults[0]
+    if args.seconds is None:
+        args.seconds = defaults[1]
     if args.warmup < 3:
         args.warmup = 3
 
@@ -202,6 +307,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
+        if WORKLOAD == "config5":
+            args.streams = args.unique
         run_reference(args, rank, world)
         return
 
@@ -214,79 +321,115 @@ def main():
     if not torch.cuda.is_available() or af.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    join = Join(world)
+    if WORKLOAD == "config5":
+        import bench_config5
+        bench_config5.run(args, rank, world, local, join)
+        join.close()
+        return
 
-    def barrier():
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
+    # host threads of this rank: the box's CPUs are shared by the ranks
     threads = max(1, host_threads() // max(1, min(world, 8)))
     t0 = time.perf_counter()
     streams = gen_streams(range(rank * args.streams, (rank + 1) * args.streams), args.seconds, threads)
     t_gen = time.perf_counter() - t0
     datas = [s.data for s in streams]
 
-    def prepass():
-        with ThreadPoolExecutor(threads) as ex:
-            return list(ex.map(af.Scan, datas))
-
     t0 = time.perf_counter()
-    scans = prepass()
+    with ThreadPoolExecutor(threads) as ex:
+        scans = list(ex.map(af.Scan, datas))
     t_scan = time.perf_counter() - t0
     audio_s = sum(s.delivered_samples / s.channels / s.samplerate for s in scans)
     n_grch = sum(s.granules * s.channels for s in scans)
+    n_grch_stereo = sum(s.granules * s.channels for s in scans if s.channels == 2)
 
     ctx = af.Context(local)
     hb = api.HostBatch(scans)
-    # inputs live in pinned host memory (H2D source of every e2e step)
-    pin_blob = torch.empty(hb.blob.size, dtype=torch.uint8).pin_memory()
-    pin_blob.numpy()[:] = hb.blob
-    pin_desc = torch.empty(hb.descs.size * 16, dtype=torch.uint8).pin_memory()
-    pin_desc.numpy()[:] = hb.descs.view(np.uint8)
-    hb.blob = pin_blob.numpy()
-    hb.descs = pin_desc.numpy().view(api.GRCH_DTYPE)
+    # inputs live in pinned host memory
+    pin_in = api.PinnedBuffer(hb.blob.size + hb.descs.size * 16 + 128, near_device=local)
+    pin_in.u8[:hb.blob.size] = hb.blob
+    doff = (hb.blob.size + 63) & ~63
+    pin_in.u8[doff:doff + hb.descs.size * 16] = hb.descs.view(np.uint8)
+    hb.blob = pin_in.u8[:hb.blob.size]
+    hb.descs = pin_in.u8[doff:doff + hb.descs.size * 16].view(api.GRCH_DTYPE)
+    spans = [(int(sd["pcm_off"]), int(sd["pcm_count"])) for sd in hb.streams]
     rb = ctx.upload(hb)
     ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=torch.device("cuda", local))
 
-    # ---- device-resident timing: W warm-up steps, then EXACTLY K timed steps ------------------------
-    for _ in range(args.warmup):
-        rb.run()
-    rb.sync()
+    def timed_steps(rbatch, steps, warmup):
+        for _ in range(warmup):
+            rbatch.run()
+        rbatch.sync()
+        join.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(ext)
+        for _ in range(steps):
+            rbatch.run()
+        ev1.record(ext)
+        rbatch.sync()
+        join.barrier()
+        step = join.max(ev0.elapsed_time(ev1) / steps)
+        nk = min(steps, 64)
+        kern, launches = rbatch.timing(nk)
+        return step, [k / nk for k in kern], launches // nk
+
+    # ---- device-resident timing, bit-exact path: W warm-up steps, then EXACTLY K timed steps ------------------------
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(ext)
-    for _ in range(args.steps):
-        rb.run()
-    ev1.record(ext)
-    rb.sync()
-    barrier()
+    step_ms, kern_ms, launches_per_step = timed_steps(rb, args.steps, args.warmup)
     clocks = sampler.stop()
-    step_ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
-    kern_ms, launches = rb.timing(min(args.steps, 64))
-    nk = min(args.steps, 64)
-    total_audio = sum_over_ranks(audio_s)
+    total_audio = join.sum(audio_s)
     value = total_audio / (step_ms * 1e-3)
+    ent_ms, gran_ms = kern_ms[0], kern_ms[1]
+
+    # the measured batch, kept on the host for the checks below (pinned: also the e2e destination)
+    pin_pcm = api.PinnedBuffer(4 * (hb.pcm_floats + 8 * (len(scans) // args.e2e_wave + 2) + 1024), near_device=local)
+    out_f32 = pin_pcm.view(np.float32)
+    rb.download_into(out_f32.ctypes.data, 0, hb.pcm_floats)
+    crc_resident = stream_crcs(out_f32, spans, threads)
+
+    # ---- parity of the measured batch: a seeded sample of streams against the oracle, bit for bit -------------------
+    import oracle
+    oracle.build()
+    rng = np.random.default_rng(20261017 + rank)
+    sample = sorted(rng.choice(len(streams), min(args.parity_sample, len(streams)), replace=False).tolist())
+
+    def oracle_pcm(i):
+        return oracle.transcode_loop(streams[i].data, 1024, keep=True)[3]
+
+    with ThreadPoolExecutor(threads) as ex:
+        refs = dict(zip(sample, ex.map(oracle_pcm, sample)))
+    mism = 0
+    for i in sample:
+        o, n = spans[i]
+        got = out_f32[o:o + n]
+        ref = refs[i].reshape(-1)
+        if got.size != ref.size or not np.array_equal(got.view(np.uint32), ref.view(np.uint32)):
+            mism += 1
+    parity = {"oracle_sample_streams": len(sample), "oracle_sample_mismatches": mism, "oracle_compare": "float PCM, bit-identical",
+              "sample_seeds": [rank * args.streams + i for i in sample]}
+
+    # ---- tolerance-mode (FMA-contracted) granule kernel: time and deviation on the same batch --------------------------
+    fused = None
+    if not args.no_fused:
+        rb.free()
+        hb.flags = api.MATH_FUSED
+        rbf = ctx.upload(hb)
+        fstep_ms, fkern_ms, _ = timed_steps(rbf, max(3, min(args.steps, 10)), 3)
+        mx, ident, cnt = 0.0, 0, 0
+        for i in sample:
+            o, n = spans[i]
+            got = rbf.download(o, n)
+            ref = refs[i].reshape(-1)
+            mx = max(mx, float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max()))
+            ident += int((q16(got) == q16(ref)).sum()); cnt += n
+        fused = {"ms_per_launch": fkern_ms[1], "ms_per_step": fstep_ms, "value": total_audio / (fstep_ms * 1e-3),
+                 "max_abs_delta_fs": mx, "identical_after_q16": ident / max(1, cnt), "compared_samples": cnt,
+                 "north_star_bar": "max |delta| <= 1e-5 FS and >= 99.99 % identical after 16-bit quantisation",
+                 "meets_bar": bool(mx <= 1e-5 and ident / max(1, cnt) >= 0.9999)}
+        rbf.free()
+        hb.flags = 0
+        rb = None
 
     # ---- roofline of the dominant kernel (granule kernel) ----------------------------------------------
     peaks = {}
@@ -294,111 +437,124 @@ def main():
     if pk.exists():
         peaks = json.loads(pk.read_text())
     hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
-    gran_ms = kern_ms[1] / nk          # sum of the granule launches of a step, timed in situ (they overlap entropy launches)
-    ent_ms = kern_ms[0] / nk           # entropy launches of a step, first start to last end
     pcm_bytes = hb.pcm_floats * 4
     alg_bytes = pcm_bytes + int(hb.blob.size)          # PCM out + bitstream in (descriptors separate)
-    achieved_gbs = alg_bytes / (gran_ms * 1e-3) / 1e9
-    fp32_tflops = n_grch * FLOPS_PER_GRCH / (gran_ms * 1e-3) / 1e12
+    flops = n_grch * FLOPS_PER_GRCH
     hbm_ceiling = hbm_peak * 1e9 / (alg_bytes / audio_s)              # audio-s/s if HBM-bound
-    fp32_ceiling = FP32_NOMINAL_TFLOPS * 1e12 / (n_grch * FLOPS_PER_GRCH / audio_s)
-    # DRAM traffic of the same kernel on the same workload, from one `ncu --set full` capture (profiles/r01_traffic.json);
-    # only quoted when this run IS that workload
+    fp32_ceiling = FP32_NOMINAL_TFLOPS * 1e12 / (flops / audio_s)
+    slower = "fp32" if fp32_ceiling < hbm_ceiling else "hbm"
     traffic = None
-    tf = ROOT / "profiles" / "r01b_traffic.json"
-    if tf.exists() and args.streams == 1024 and args.seconds == 60.0:
+    tf = ROOT / "profiles" / TRAFFIC_FILE
+    if tf.exists() and WORKLOAD == "config2" and args.streams == 1024 and args.seconds == 60.0:
         traffic = json.loads(tf.read_text()).get("granule", {}).get("traffic")
-    roofline = {"bound": "hbm", "kernel": "l3_granule_kernel<2,4>", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "peak_source": "measured" if peaks else "fallback", "traffic": traffic,
-                "traffic_note": "ncu dram read+write per launch; above the algorithmic bytes because the kernel reads the int16 "
-                                "spectra and the 256-byte scalefactor/gain records written by the entropy kernels",
-                "ms_per_launch": gran_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "fp32": {"achieved_tflops": fp32_tflops, "peak_tflops_nominal": FP32_NOMINAL_TFLOPS,
-                         "frac": fp32_tflops / FP32_NOMINAL_TFLOPS,
-                         "unfused_pipe_peak_tflops_measured": FP32_UNFUSED_MEASURED_TFLOPS,
-                         "frac_of_unfused_pipe_peak": fp32_tflops / FP32_UNFUSED_MEASURED_TFLOPS,
-                         "note": "flops counted un-fused (32,734 per granule-channel); the kernel is compiled -fmad=false for "
-                                 "bit-exactness, so every flop takes one FP32-pipe lane slot: the measured un-fused pipe peak "
-                                 "(tools/microbench/fp32_pipes.cu) is its real ceiling, half the FMA-counted nominal one"},
-                "slower_roof": "fp32" if fp32_ceiling < hbm_ceiling else "hbm",
-                "frac_of_slower_roof_whole_step": (audio_s / (step_ms * 1e-3)) / min(fp32_ceiling, hbm_ceiling) if world == 1 else None,
-                "entropy_kernels_ms": ent_ms, "granule_kernel_share_of_step": min(1.0, gran_ms / (kern_ms[2] / nk)),
-                "kernels": ["l3_scf_kernel", "l3_huff_big_kernel<16,8>", "l3_huff_c1_kernel<16>", "l3_granule_kernel<2,4>"],
+
+    def roof(ms):
+        gbs, tfl = alg_bytes / (ms * 1e-3) / 1e9, flops / (ms * 1e-3) / 1e12
+        return {"ms_per_launch": ms, "hbm_gbs": gbs, "hbm_frac_of_measured": gbs / hbm_peak, "fp32_tflops": tfl,
+                "fp32_frac_of_nominal": tfl / FP32_NOMINAL_TFLOPS, "frac_of_slower_roof": (tfl / FP32_NOMINAL_TFLOPS) if slower == "fp32" else gbs / hbm_peak}
+
+    r_exact = roof(gran_ms)
+    roofline = {"bound": slower, "kernel": "l3_granule_kernel<2,4,exact>", "slower_roof": slower,
+                "achieved": r_exact["fp32_tflops"] if slower == "fp32" else r_exact["hbm_gbs"],
+                "peak": FP32_NOMINAL_TFLOPS if slower == "fp32" else hbm_peak, "unit": "TFLOP/s" if slower == "fp32" else "GB/s",
+                "frac": r_exact["frac_of_slower_roof"],
+                "peak_source": "nominal FP32 (148 SM x 128 lanes x 2 x 1.965 GHz; the driver measures no FP32 peak)" if slower == "fp32"
+                               else ("measured" if peaks else "fallback"),
+                "flops_counted": "reference operation count, 32,734 add/sub/mul per granule-channel (SURVEY 8d); an FMA-capable peak counts 2 per lane-slot",
+                "hbm": {"achieved_gbs": r_exact["hbm_gbs"], "peak_gbs": hbm_peak, "frac": r_exact["hbm_frac_of_measured"],
+                        "peak_source": "measured" if peaks else "fallback", "algorithmic_bytes_per_launch": alg_bytes},
+                "traffic": traffic, "traffic_source": f"profiles/{TRAFFIC_FILE} (ncu dram read+write per launch, same workload)" if traffic else None,
+                "ms_per_launch": gran_ms,
+                "bit_exact": {**r_exact, "unfused_pipe_peak_tflops_measured": FP32_UNFUSED_MEASURED_TFLOPS,
+                              "frac_of_unfused_pipe_peak": r_exact["fp32_tflops"] / FP32_UNFUSED_MEASURED_TFLOPS,
+                              "note": "every product and sum rounded separately (bit-identical PCM): each flop takes one FP32-pipe lane slot, "
+                                      "so the measured un-fused pipe peak (tools/microbench/fp32_pipes.cu) is this mode's ceiling, half the FMA-counted nominal"},
+                "fused": ({**roof(fused["ms_per_launch"]), **{k: fused[k] for k in ("max_abs_delta_fs", "identical_after_q16", "meets_bar", "north_star_bar", "compared_samples")},
+                           "whole_step_value": fused["value"]} if fused else None),
+                "frac_of_slower_roof_whole_step": (total_audio / (step_ms * 1e-3)) / (world * min(fp32_ceiling, hbm_ceiling)),
+                "entropy_kernels_ms": ent_ms, "granule_kernel_share_of_step": min(1.0, gran_ms / kern_ms[2]),
+                "kernels": ["l3_scf_kernel", "l3_huff_big_kernel<16,8>", "l3_huff_c1_kernel<16>", "l3_granule_kernel<2,4,exact>"]
+                           + (["l3_granule_kernel<1,4,exact>"] if n_grch_stereo != n_grch else []),
                 "kernels_note": "one launch of each per step, in that order; entropy_kernels_ms spans the first three"}
 
-    # ---- end to end: MP3 bytes (host) -> PCM floats (pinned host) ------------------------------------------
-    # Through the public batch API (audio_formats_b200.BatchPipeline): per wave host prepass (frame sync, side
-    # info, reservoir slicing) -> H2D from pinned staging -> entropy + granule kernels -> D2H into pinned memory,
-    # waves overlapped across `lanes` contexts/streams.
+    # ---- end to end: MP3 bytes (host) -> PCM (pinned host), through the library's pipeline ------------------------------
     e2e = None
     if not args.no_e2e:
-        rb.free()
-        rb = None
-        pin_pcm = api.PinnedBuffer(4 * (hb.pcm_floats + 4 * len(scans) + 1024))
-        out = pin_pcm.view(np.float32)
-        pipe = af.BatchPipeline(device=local, lanes=args.e2e_lanes, wave_streams=args.e2e_wave, prepass_threads=threads)
-        info = pipe.decode_into(datas, out)          # warm-up (allocates the recycled workspaces)
-        pipe.decode_into(datas, out)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            info = pipe.decode_into(datas, out)
-        barrier()
-        e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
-        # spot-check the delivered PCM against the device-resident run's checksum source (first stream)
-        o0, f0, c0, _ = info[0]
+        if rb is not None:
+            rb.free()
+            rb = None
         h2d = int(hb.blob.size) + hb.descs.size * 16 + hb.streams.size * 56
-        e2e = {"value": total_audio / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": pcm_bytes,
-               "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
-               "pipeline": {"lanes": args.e2e_lanes, "wave_streams": args.e2e_wave, "host_prepass_threads": threads},
-               "includes": "host prepass + H2D (pinned) + kernels + D2H (pinned) of every step",
-               "first_stream_abs_sum": float(np.abs(out[o0:o0 + f0 * c0].astype(np.float64)).sum())}
-        pipe.close()
-        pin_pcm.free()
-        # what the copy engine can do on this box: 1 GiB device -> pinned host, best of 3 (the e2e step moves d2h_bytes_per_step)
-        try:
-            src = torch.empty(1 << 28, dtype=torch.float32, device="cuda")
-            dst = torch.empty(1 << 28, dtype=torch.float32).pin_memory()
-            best = 0.0
-            for _ in range(3):
-                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                c0.record(); dst.copy_(src, non_blocking=True); c1.record(); torch.cuda.synchronize()
-                best = max(best, (1 << 30) / (c0.elapsed_time(c1) * 1e-3) / 1e9)
-            del src, dst
-            e2e["d2h_pinned_peak_gbs"] = best
-        except RuntimeError as exc:   # a side measurement must not take the bench down
-            e2e["d2h_pinned_peak_gbs"] = None
-            e2e["d2h_pinned_peak_error"] = str(exc)[:200]
-        e2e["d2h_achieved_gbs"] = pcm_bytes / e2e_s / 1e9
-        e2e["bound"] = "PCIe device->host copy of the float PCM (kernels are hidden behind it)"
 
-    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same workload ---------------
+        def run_e2e(s16, steps):
+            pipe = af.BatchPipeline(device=local, lanes=args.e2e_lanes, wave_streams=args.e2e_wave, prepass_threads=threads, s16=s16)
+            out = pin_pcm.view(np.int16) if s16 else out_f32
+            info = pipe.decode_into(datas, out)          # warm-up (allocates the recycled workspaces)
+            pipe.profile()
+            join.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                info = pipe.decode_into(datas, out)
+            join.barrier()
+            sec = join.max((time.perf_counter() - t0) / steps)
+            prof = pipe.profile()
+            pipe.close()
+            return sec, info, {k: v / steps for k, v in prof.items()}, out
+
+        # 16-bit delivery (headline): compare a sample with q16(oracle) and every stream with q16 of the resident run
+        sec16, info16, prof16, out16 = run_e2e(True, args.e2e_steps)
+        bad16 = 0
+        for i in sample:
+            o, fr, ch, _hz = info16[i]
+            if not np.array_equal(out16[o:o + fr * ch], q16(refs[i].reshape(-1))):
+                bad16 += 1
+        parity["e2e_s16_sample_mismatches"] = bad16
+        # float delivery: every stream's checksum against the device-resident run (a second, differently batched decode)
+        sec32, info32, prof32, _ = run_e2e(False, max(2, args.e2e_steps - 1))
+        crc_e2e = stream_crcs(out_f32, [(o, fr * ch) for (o, fr, ch, _hz) in info32], threads)
+        parity["crc_streams_checked"] = len(crc_e2e)
+        parity["crc_mismatches"] = int(sum(a != b2 for a, b2 in zip(crc_e2e, crc_resident)))
+        parity["crc_compare"] = "crc32 of every stream's float PCM: device-resident run vs the wave pipeline's decode"
+        d2h16 = hb.pcm_floats * 2
+        peak = d2h_rate_gbs(torch, join)
+        e2e = {"value": total_audio / sec16, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h16,
+               "ms_per_step": sec16 * 1e3, "steps": args.e2e_steps, "output": "int16 PCM in pinned host memory (L3B_OUT_S16)",
+               "pipeline": {"lanes": args.e2e_lanes, "wave_streams": args.e2e_wave, "scan_threads": threads,
+                            "seconds_per_step_by_phase_summed_over_threads": prof16},
+               "includes": "host prepass + H2D (pinned) + kernels + D2H (pinned) of every step, through l3b_pipeline_decode",
+               "d2h_achieved_gbs": d2h16 / sec16 / 1e9,
+               "d2h_concurrent_peak_gbs": peak, "d2h_concurrent_peak_aggregate_gbs": None if peak is None else peak * world,
+               "d2h_peak_note": "1 GiB device->pinned copy, every rank at the same time between two barriers, slowest rank, best of 3",
+               "f32": {"value": total_audio / sec32, "ms_per_step": sec32 * 1e3, "d2h_bytes_per_step": pcm_bytes,
+                       "d2h_achieved_gbs": pcm_bytes / sec32 / 1e9, "output": "float PCM in pinned host memory",
+                       "seconds_per_step_by_phase_summed_over_threads": prof32}}
+    pin_pcm.free()
+
+    # ---- CPU baseline (rank 0): the oracle on a bounded sample of the same workload ---------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         ht = host_threads()
         a1, w1 = cpu_decode_throughput(streams[:1], 1)
-        per_stream = w1
-        n_sample = int(max(ht, min(len(streams), args.cpu_baseline_seconds * ht / max(per_stream, 1e-6))))
+        n_sample = int(max(ht, min(len(streams), args.cpu_baseline_seconds * ht / max(w1, 1e-6))))
         a, w = cpu_decode_throughput(streams[:n_sample], ht)
         cpu = {"value": a / w, "unit": UNIT, "cores": ht, "kind": "port",
-               "sample": f"first {n_sample} of the {len(streams)} streams, {args.seconds:g} s each, transcode loop (1024-frame reads)",
-               "single_thread_value": a1 / w1,
-               "note": "C restatement of the reference's D decoder (no D compiler in this image)"}
+               "sample": f"first {n_sample} of the {len(streams)} streams of rank 0, {args.seconds:g} s each",
+               "single_thread_value": a1 / w1, "note": cpu_baseline_note()}
+    join.barrier()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(args, args.streams),
+                "data": "synthetic", "config": workload_config(args),
                 "audio_seconds_per_step": total_audio, "granule_channels_per_gpu": n_grch,
-                "clocks": clocks, "gpu_launches": launches if nk == args.steps else int(launches * args.steps / nk),
-                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-                "setup": {"generate_s": t_gen, "prepass_s": t_scan, "host_threads": threads}}
+                "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "parity": parity,
+                "setup": {"generate_s": t_gen, "prepass_s": t_scan, "host_threads": threads,
+                          "join": "gloo (timing scalars only; no NCCL, no collective on the data path)" if world > 1 else "single process"}}
         print(json.dumps(line), flush=True)
     if rb is not None:
         rb.free()
     ctx.close()
-    if dist:
-        dist.destroy_process_group()
+    join.close()
 
 
 if __name__ == "__main__":

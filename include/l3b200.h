@@ -74,7 +74,19 @@ typedef struct {
     int16_t* is;      /* [n_grch][576] signed quantised values (the reference's fused Huffman never materialises these) */
     uint8_t* iscf;    /* [n_grch][40]  integer scalefactors after subblock_gain / preflag (minimp3.d:694-712) */
     uint8_t* ist_pos; /* [n_grch][40]  intensity positions as left by L3_decode_scalefactors */
+    /* Float stage snapshots of the bit-exact pipeline, [n_grch][576] each, written for the granules whose PCM is
+     * delivered (granules wholly inside the encoder delay stay zero).  Same points as the oracle's taps: */
+    float* xr;        /* after Huffman + requantisation, before stereo processing (after minimp3.d:1205) */
+    float* st;        /* after MS / intensity stereo (after minimp3.d:1213) */
+    float* im;        /* after reorder / alias reduction / IMDCT / frequency inversion (after minimp3.d:1229), [band][18] */
+    float* dct;       /* after mp3d_DCT_II (after minimp3.d:1414), the reference's in-place layout [output j][slot] */
 } l3b_taps_t;
+
+/* l3b_batch_t.flags */
+#define L3B_OUT_S16 1u     /* deliver 16-bit PCM: q = clamp(lrintf(x * 32768), -32768, 32767) of the float sample x (the
+                              un-dithered float -> s16 conversion of the reference's WAV writer, wav.d:475-700); `pcm` is int16_t* */
+#define L3B_MATH_FUSED 2u  /* tolerance mode: multiply-adds contracted into FMAs (faster, NOT bit-identical to the reference;
+                              within 1e-5 of full scale).  Default (0) is the bit-exact pipeline. */
 
 typedef struct {
     const uint8_t* maindata;          /* batch blob: HOST memory (copied in) */
@@ -83,10 +95,12 @@ typedef struct {
     uint64_t n_grch;
     const l3b_stream_desc_t* streams; /* HOST */
     uint32_t n_streams;
-    float* pcm;                       /* HOST destination, interleaved float, sum(pcm_count) floats laid out by pcm_off */
-    uint64_t pcm_floats;
+    void* pcm;                        /* HOST destination, interleaved: float (default) or int16_t (L3B_OUT_S16); laid out by pcm_off */
+    uint64_t pcm_floats;              /* samples (elements) in `pcm` */
     int32_t* status;                  /* HOST, optional [n_streams]: 0 or negative code per stream */
     const l3b_taps_t* taps;           /* optional */
+    uint32_t flags;                   /* L3B_OUT_S16 | L3B_MATH_FUSED */
+    uint32_t reserved;
 } l3b_batch_t;
 
 typedef struct l3b_ctx l3b_ctx_t;
@@ -100,6 +114,9 @@ const char* l3b_last_error(const l3b_ctx_t* ctx); /* ctx may be NULL: last error
 /* Page-locked host memory for batch inputs / PCM outputs (cudaHostAlloc): copies from and to it run at full PCIe
  * speed and asynchronously.  Returns NULL on failure. */
 void* l3b_host_alloc(size_t bytes);
+/* The same, with the pages placed on the NUMA node the GPU `device_id` hangs off (read from sysfs through the device's
+ * PCI address; falls back to l3b_host_alloc when the topology cannot be read). */
+void* l3b_host_alloc_near(int device_id, size_t bytes);
 void l3b_host_free(void* p);
 
 /* Decode a whole batch, host buffers in / host buffers out (H2D + kernels + D2H inside). */
@@ -117,7 +134,9 @@ int l3b_batch_upload_reuse(l3b_ctx_t* ctx, const l3b_batch_t* batch, l3b_residen
 int l3b_batch_reupload(l3b_ctx_t* ctx, l3b_resident_t* r, const l3b_batch_t* batch);
 int l3b_batch_run(l3b_ctx_t* ctx, l3b_resident_t* r);                      /* async on the context stream */
 int l3b_batch_sync(l3b_ctx_t* ctx);
-int l3b_batch_download(l3b_ctx_t* ctx, l3b_resident_t* r, float* pcm_host, uint64_t first_float, uint64_t n_floats);
+/* Copies samples [first, first + n) of the batch's PCM (float or int16_t elements, as uploaded) and waits for them.
+ * The wait sleeps (cudaEventBlockingSync): a lane blocked on its copy does not occupy a host core. */
+int l3b_batch_download(l3b_ctx_t* ctx, l3b_resident_t* r, void* pcm_host, uint64_t first, uint64_t n);
 int l3b_batch_download_taps(l3b_ctx_t* ctx, l3b_resident_t* r, const l3b_taps_t* taps);
 void* l3b_batch_device_pcm(l3b_resident_t* r);                              /* raw device pointer (for checksums/tests) */
 void l3b_batch_free(l3b_ctx_t* ctx, l3b_resident_t* r);
@@ -161,10 +180,47 @@ int l3b_scans_assemble(l3b_scan_t* const* scans, uint32_t n, uint8_t* blob, uint
  * pcm[i] must have room for l3b_scan_delivered_samples(scans[i]) floats. */
 int l3b_decode_scans(l3b_ctx_t* ctx, l3b_scan_t* const* scans, uint32_t n, float* const* pcm, int32_t* status);
 
+/* Batch entry point over RAW streams, pipelined in waves over one or more GPUs (l3_pipeline.cpp): MP3 bytes in host memory
+ * in, PCM in host memory out (float, or int16_t with L3B_OUT_S16).  Per GPU `lanes` contexts (CUDA stream + recycled device
+ * workspace + pinned staging each) run assemble -> H2D -> kernels -> D2H for their waves of `wave_streams` streams while
+ * `scan_threads` host threads run the prepass (l3b_scan_memory) ahead of them.  With several devices the streams are assigned
+ * by file, longest first, with no collective on the data path (streams are independent: minimp3.d:38-46).
+ * A stream that cannot be decoded gets its status and zero frames; the others are unaffected. */
+typedef struct l3b_pipeline l3b_pipeline_t;
+typedef struct {
+    int32_t lanes;         /* per device; <= 0: 4 */
+    int32_t wave_streams;  /* <= 0: 16 */
+    int32_t scan_threads;  /* <= 0: host CPUs available to the process minus one per device */
+    uint32_t flags;        /* L3B_OUT_S16 | L3B_MATH_FUSED */
+} l3b_pipeline_opts_t;
+typedef struct {
+    uint64_t pcm_off;      /* element offset of the stream's first delivered sample in the output buffer */
+    uint64_t frames;       /* frames delivered (samples per channel) */
+    int32_t channels, samplerate;
+    int32_t status;        /* 0, or the negative code that made the stream undecodable / stopped it early */
+    int32_t device;        /* GPU that decoded it */
+} l3b_stream_result_t;
+#define L3B_PIPELINE_PHASES 6
+int l3b_pipeline_create(const int* device_ids, int n_devices, const l3b_pipeline_opts_t* opts, l3b_pipeline_t** out);
+void l3b_pipeline_destroy(l3b_pipeline_t* p);
+/* `out` should be page-locked (l3b_host_alloc_near) and hold `out_capacity` elements; every wave's PCM starts 16-byte aligned,
+ * so allow 8 elements of slack per wave.  *out_used (optional) receives the elements handed out. */
+int l3b_pipeline_decode(l3b_pipeline_t* p, const uint8_t* const* data, const size_t* size, uint32_t n, void* out,
+                        uint64_t out_capacity, l3b_stream_result_t* results, uint64_t* out_used);
+/* Seconds per phase summed over threads since the last call: [0] host prepass (scan threads), then per lane [1] assemble,
+ * [2] upload, [3] launch, [4] PCM download incl. waiting for the kernels, [5] waiting for the prepass. */
+int l3b_pipeline_profile(l3b_pipeline_t* p, double seconds[L3B_PIPELINE_PHASES]);
+const char* l3b_pipeline_last_error(const l3b_pipeline_t* p);
+
 /* AudioStream mirror (names follow stream.d). */
 typedef struct l3b_stream l3b_stream_t;
 int l3b_stream_open_memory(l3b_ctx_t* ctx, const uint8_t* data, size_t size, l3b_stream_t** out); /* stream.d:150 (copies input) */
 int l3b_stream_open_file(l3b_ctx_t* ctx, const char* path, l3b_stream_t** out);                   /* stream.d:115 */
+/* The reference's callback I/O (mp3dec_io_t, minimp3_ex.d:61-71; stream.d:2243-2254 wires IOCallbacks onto it): `read`
+ * returns the bytes read (short = end of input), `seek` 0 on success.  The callbacks are drained into memory inside the call. */
+typedef size_t (*l3b_read_cb)(void* buf, size_t size, void* user);
+typedef int (*l3b_seek_cb)(uint64_t position, void* user);
+int l3b_stream_open_callbacks(l3b_ctx_t* ctx, l3b_read_cb read, l3b_seek_cb seek, void* user, l3b_stream_t** out); /* mp3dec_ex_open_cb, minimp3_ex.d:929 */
 void l3b_stream_close(l3b_stream_t* s);
 int l3b_stream_num_channels(const l3b_stream_t* s);      /* stream.d:396 */
 int64_t l3b_stream_length_frames(const l3b_stream_t* s); /* stream.d:402 */

@@ -63,6 +63,9 @@ def lib():
         L.l3o_transcode_loop.restype = C.c_longlong
         L.l3o_transcode_loop.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.l3o_transcode_loop_s16.restype = C.c_longlong
+        L.l3o_transcode_loop_s16.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
+                                             C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.l3o_set_tap.argtypes = [C.c_void_p]
         L.l3o_enable_timers.argtypes = [C.c_int]
         L.l3o_get_timers.argtypes = [C.POINTER(C.c_double * 7)]
@@ -133,10 +136,14 @@ def decode_all(data: bytes, chunk_frames: int = 1024, taps: int = 0):
     return pcm, None
 
 
-def transcode_loop(data: bytes, chunk_frames: int = 1024, keep: bool = False):
-    """Whole decode inside C (GIL released): returns (frames, channels, hz, pcm or None)."""
+def transcode_loop(data: bytes, chunk_frames: int = 1024, keep: bool = False, s16: bool = False):
+    """Whole decode inside C (GIL released): returns (frames, channels, hz, pcm or None).
+    s16: every chunk is also converted to 16 bit (un-dithered), the result discarded (keep is ignored)."""
     L = lib()
     nch, hz = C.c_int(), C.c_int()
+    if s16:
+        n = L.l3o_transcode_loop_s16(data, len(data), chunk_frames, None, 0, C.byref(nch), C.byref(hz))
+        return n, nch.value, hz.value, None
     if keep:
         probe = OracleStream(data)
         cap = int(probe.length_frames) * probe.channels + 2304 * 4

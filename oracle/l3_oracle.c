@@ -459,10 +459,11 @@ static void huffman(float* dst, bitrd_t* bs, const gr_info_t* gr_info, const flo
                         HB_REFILL(hb);
                         *dst = one * pow_43(lsb) * ((int32_t)hb.cache < 0 ? -1 : 1);
                     } else {
-                        /* reference: g_pow43[16 + lsb - 16*sign]*one, the table's lower half being the
-                         * exact negation of the upper half */
+                        /* reference (minimp3.d:816): g_pow43[16 + lsb - 16*sign]*one.  The table's lower half is the
+                         * negation of the upper half EXCEPT entry 0, which is +0 in both (minimp3.d:722-724): a zero
+                         * coefficient followed by a 1 bit stays +0.0, it does not become -0.0 */
                         float p43 = L3_POW43[lsb];
-                        *dst = ((hb.cache >> 31) ? -p43 : p43) * one;
+                        *dst = ((hb.cache >> 31) && lsb ? -p43 : p43) * one;
                     }
                     if (tap_is) tap_is[dst - dst0] = (int16_t)((lsb && (hb.cache >> 31)) ? -lsb : lsb);
                     HB_FLUSH(hb, lsb ? 1 : 0);

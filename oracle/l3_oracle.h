@@ -140,6 +140,10 @@ int l3o_stream_last_error(const l3o_stream_t* s);
 long long l3o_transcode_loop(const uint8_t* data, size_t size, int chunk_frames, float* out, size_t cap_samples,
                              int* channels_out, int* hz_out);
 
+/* the same with the un-dithered float -> s16 conversion per chunk (wav.d:475-700) */
+long long l3o_transcode_loop_s16(const uint8_t* data, size_t size, int chunk_frames, int16_t* out16, size_t cap_samples,
+                                 int* channels_out, int* hz_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@
  * stream.d:1706-1749 uses): ID3/APE skipping, detection, VBR-tag probe, whole-file index, sample
  * accurate seek with reservoir pre-roll, and the buffered read loop.  PARITY UNPINNED (see header).
  */
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -522,6 +523,45 @@ long long l3o_transcode_loop(const uint8_t* data, size_t size, int chunk_frames,
         total += n;
     }
     free(chunk);
+    l3o_stream_close(s);
+    return total;
+}
+
+/* The same loop with the un-dithered float -> 16-bit conversion the reference's WAV writer applies per chunk
+ * (wav.d:475-700 without its rand() dither; q = clamp(lrintf(x * 32768), -32768, 32767)): what a transcode to
+ * 16-bit WAV costs on the CPU.  out16 may be NULL (the converted chunk is then discarded, but still computed). */
+long long l3o_transcode_loop_s16(const uint8_t* data, size_t size, int chunk_frames, int16_t* out16, size_t cap_samples,
+                                 int* channels_out, int* hz_out)
+{
+    l3o_stream_t* s = l3o_stream_open_memory(data, size);
+    if (!s) return -1;
+    int nch = s->channels;
+    if (channels_out) *channels_out = nch;
+    if (hz_out) *hz_out = s->samplerate;
+    float* chunk = (float*)malloc(sizeof(float) * (size_t)chunk_frames * (size_t)nch);
+    int16_t* chunk16 = (int16_t*)malloc(sizeof(int16_t) * (size_t)chunk_frames * (size_t)nch);
+    long long total = 0;
+    size_t at = 0;
+    volatile int16_t sink = 0;
+    for (;;) {
+        int n = l3o_stream_read_float(s, chunk, chunk_frames);
+        if (n <= 0) break;
+        size_t cnt = (size_t)n * (size_t)nch;
+        for (size_t i = 0; i < cnt; i++) {
+            long q = lrintf(chunk[i] * 32768.0f);
+            chunk16[i] = (int16_t)(q < -32768 ? -32768 : (q > 32767 ? 32767 : q));
+        }
+        sink = chunk16[cnt - 1];
+        if (out16) {
+            if (at + cnt > cap_samples) cnt = cap_samples - at;
+            memcpy(out16 + at, chunk16, cnt * sizeof(int16_t));
+            at += cnt;
+        }
+        total += n;
+    }
+    (void)sink;
+    free(chunk);
+    free(chunk16);
     l3o_stream_close(s);
     return total;
 }
