@@ -351,6 +351,10 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
         CU_TRY_R(cudaMalloc(&r->d_nzc, r->cap_grch + 16));
     }
     const bool want_ftaps = b->taps && (b->taps->xr || b->taps->st || b->taps->im || b->taps->dct);
+    if (want_ftaps && (flags & (L3B_OUT_S16 | L3B_MATH_FUSED))) {
+        c->err = "float taps exist in the bit-exact float-delivery mode only";
+        return bail(L3B_E_PARAM);
+    }
     if (want_ftaps && !r->d_ftaps) {
         CU_TRY_R(cudaMalloc(&r->d_ftaps, r->cap_grch * 4 * 576 * sizeof(float)));
         CU_TRY_R(cudaMemsetAsync(r->d_ftaps, 0, r->cap_grch * 4 * 576 * sizeof(float), c->stream));

@@ -19,7 +19,6 @@ __constant__ float c_pan[14];
 // (1.0f, 1.0f), written at context creation.  ptxas cannot know its value, so FFMA2(a, c_one2, b) stays what it is:
 // a packed add that rounds exactly like add.rn (a * 1 is exact).  See VT<2, false>.
 __constant__ float2 c_one2;
-__constant__ float2 c_neg_one2;   // (-1, -1): the same for the packed subtraction
 
 void upload_constants() {
     cudaMemcpyToSymbol(c_expfrac, L3_EXPFRAC, sizeof c_expfrac);
@@ -29,9 +28,8 @@ void upload_constants() {
     cudaMemcpyToSymbol(c_mdctw, L3_MDCT_WINDOW, sizeof c_mdctw);
     cudaMemcpyToSymbol(c_sec, L3_SEC, sizeof c_sec);
     cudaMemcpyToSymbol(c_pan, L3_PAN, sizeof c_pan);
-    const float2 one = make_float2(1.0f, 1.0f), neg_one = make_float2(-1.0f, -1.0f);
+    const float2 one = make_float2(1.0f, 1.0f);
     cudaMemcpyToSymbol(c_one2, &one, sizeof one);
-    cudaMemcpyToSymbol(c_neg_one2, &neg_one, sizeof neg_one);
 }
 
 // =====================================================================================================
@@ -53,7 +51,8 @@ void upload_constants() {
 //                  packed add into FFMA2 even under -fmad=false and explicit .rn, so the packed ADD is written as
 //                  FFMA2(a, ONE, b) with ONE = (1, 1) read from constant memory: a * 1 is exact, the sum is rounded
 //                  once, denormals and signed zeros behave like add.rn, and nothing is left for ptxas to contract.
-//                  Subtraction is FFMA2(b, -ONE, a).
+//                  Subtraction is the addition of the negated operand (a - b == a + (-b) in IEEE arithmetic, signed zeros
+//                  included), and a product to be subtracted is formed with the negated weight (a * (-w) == -(a * w)).
 //   FUSED = true   tolerance mode: multiply-adds of the reference are contracted into FFMA2 by hand (one rounding
 //                  instead of two).  Not bit-identical; measured against the north star's 1e-5 FS / 99.99 % bar.
 
@@ -103,23 +102,30 @@ template <bool FUSED> struct VT<2, FUSED> {
               "l"(*reinterpret_cast<const unsigned long long*>(&c)));
         return *reinterpret_cast<T*>(&r);
     }
+#ifdef L3B_EXP_SCALAR_MUL   // A/B only: round-1 arithmetic (scalar multiplies feeding packed adds)
+    static __device__ __forceinline__ T add(T a, T b) { return __fadd2_rn(a, b); }
+    static __device__ __forceinline__ T sub(T a, T b) { return __fadd2_rn(a, neg(b)); }
+    static __device__ __forceinline__ T muls(T a, float s) { return FUSED ? __fmul2_rn(a, bc(s)) : make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s)); }
+    static __device__ __forceinline__ T mulw(T a, float w0, float w1) { return FUSED ? __fmul2_rn(a, make_float2(w0, w1)) : make_float2(__fmul_rn(a.x, w0), __fmul_rn(a.y, w1)); }
+#else
     static __device__ __forceinline__ T add(T a, T b) { return FUSED ? __fadd2_rn(a, b) : fma_const(a, c_one2, b); }
-    static __device__ __forceinline__ T sub(T a, T b) { return FUSED ? __fadd2_rn(a, neg(b)) : fma_const(b, c_neg_one2, a); }
+    static __device__ __forceinline__ T sub(T a, T b) { return FUSED ? __fadd2_rn(a, neg(b)) : fma_const(a, c_one2, neg(b)); }   // a - b == a + (-b), exactly
     static __device__ __forceinline__ T muls(T a, float s) { return __fmul2_rn(a, bc(s)); }
     static __device__ __forceinline__ T mulw(T a, float w0, float w1) { return __fmul2_rn(a, make_float2(w0, w1)); }
+#endif
     static __device__ __forceinline__ T mac(T c, T a, float w) { return FUSED ? __ffma2_rn(a, bc(w), c) : add(c, muls(a, w)); }
-    static __device__ __forceinline__ T msc(T c, T a, float w) { return FUSED ? __ffma2_rn(a, bc(-w), c) : sub(c, muls(a, w)); }
+    static __device__ __forceinline__ T msc(T c, T a, float w) { return FUSED ? __ffma2_rn(a, bc(-w), c) : add(c, muls(a, -w)); }   // a*(-w) == -(a*w), exactly
     static __device__ __forceinline__ T mm_add(T a, float wa, T b, float wb) {
         return FUSED ? __ffma2_rn(b, bc(wb), muls(a, wa)) : add(muls(a, wa), muls(b, wb));
     }
     static __device__ __forceinline__ T mm_sub(T a, float wa, T b, float wb) {
-        return FUSED ? __ffma2_rn(b, bc(-wb), muls(a, wa)) : sub(muls(a, wa), muls(b, wb));
+        return FUSED ? __ffma2_rn(b, bc(-wb), muls(a, wa)) : add(muls(a, wa), muls(b, -wb));
     }
     static __device__ __forceinline__ T mmw_add(T a, float wa0, float wa1, T b, float wb0, float wb1) {
         return FUSED ? __ffma2_rn(b, make_float2(wb0, wb1), mulw(a, wa0, wa1)) : add(mulw(a, wa0, wa1), mulw(b, wb0, wb1));
     }
     static __device__ __forceinline__ T mmw_sub(T a, float wa0, float wa1, T b, float wb0, float wb1) {
-        return FUSED ? __ffma2_rn(b, make_float2(-wb0, -wb1), mulw(a, wa0, wa1)) : sub(mulw(a, wa0, wa1), mulw(b, wb0, wb1));
+        return FUSED ? __ffma2_rn(b, make_float2(-wb0, -wb1), mulw(a, wa0, wa1)) : add(mulw(a, wa0, wa1), mulw(b, -wb0, -wb1));
     }
     static __device__ __forceinline__ T shfl_up(T a) {
         return make_float2(__shfl_up_sync(0xffffffffu, a.x, 1), __shfl_up_sync(0xffffffffu, a.y, 1));
@@ -358,7 +364,7 @@ __device__ __noinline__ void imdct_split(float* x, float* ovl, float* y, bool sh
 
 constexpr int kCtaTableBytes = 1040 + 496 + 2048;   // s_pow43 (257 floats + pad) | s_ldexp (121 floats + pad) | s_win (16 x 32 floats)
 
-template <int NCH, int WARPS, bool FUSED, bool TAPS>
+template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16>
 __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
     typedef VT<NCH, FUSED> V;
     typedef typename V::T T;
@@ -398,6 +404,14 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
         const int l = i & 31, kc = i >> 5;
         s_win[i] = (l & 15) < 15 ? __ldg(p.t.win + kc * 15 + (l & 15)) : 0.0f;
     }
+#ifdef L3B_EXP_W_REGS   // A/B only: weights held in registers for the whole kernel
+    float w0[8], w1[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        w0[k] = ii < 15 ? __ldg(p.t.win + (k * 2 + 0) * 15 + ii) : 0.0f;
+        w1[k] = ii < 15 ? __ldg(p.t.win + (k * 2 + 1) * 15 + ii) : 0.0f;
+    }
+#endif
 
     // recompute halo: up to two granules before the tile, unless decoder state was zeroed in between
     int start = (int)tile.g0;
@@ -423,9 +437,8 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
 
     const int n_long_bands_mixed = 2 << (row == 1 ? 1 : 0);  // minimp3.d:1218
     const uint64_t skipf = S.pcm_skip / NCH, countf = S.pcm_count / NCH;   // in frames
-    // delivery: float samples, or 16-bit ones at the same element offsets (one pointer, element size by flag)
-    const bool out16 = p.pcm16 != nullptr;
-    char* const out_base = out16 ? reinterpret_cast<char*>(p.pcm16 + S.pcm_off) : reinterpret_cast<char*>(p.pcm + S.pcm_off);
+    // delivery: float samples, or (S16) 16-bit ones at the same element offsets
+    char* const out_base = S16 ? reinterpret_cast<char*>(p.pcm16 + S.pcm_off) : reinterpret_cast<char*>(p.pcm + S.pcm_off);
 
     // lane 0: TMA bulk copies of granule g's inputs into the staging buffers.  Only the chunks of the spectra that
     // hold anything are fetched: n0 / n1 = nz_chunks of the two channels (from p.nzc, read a granule ahead).
@@ -482,20 +495,22 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             // band gains (minimp3.d:714-719): scf[i] = gain * 2^(-(iscf[i] << shift)/4); `gain` = 2^(gain_exp/4) comes with
             // the record (l3_scf_kernel), the per-band factor is one table step of L3_ldexp_q2 (two or more when the
             // exponent exceeds 120, which takes a scalefactor above 30).
-            for (int i = lane; i < NCH * 40; i += 32) {
-                const int c = (NCH == 2 && i >= 40) ? 1 : 0, b = i - 40 * c;
-                const uint8_t* rc = c ? rec1 : rec0;
-                const Desc& dc = c ? d1 : d0;
-                const int kd = c ? kind1 : kind0;
-                const int n_sfb = kd == 0 ? 22 : (kd == 1 ? 39 : (mpeg1 ? 38 : 36));
-                float y = *reinterpret_cast<const float*>(rc + kSfGainOff);
-                int e = (int)rc[b] << (dc.scalefac_scale() + 1);
-                do {
-                    const int k = e < 120 ? e : 120;
-                    y = __fmul_rn(y, s_ldexp[k]);
-                    e -= k;
-                } while (e > 0);
-                W.gains[c][b] = b < n_sfb ? y : 0.0f;
+            {
+                const int nsf0 = kind0 == 0 ? 22 : (kind0 == 1 ? 39 : (mpeg1 ? 38 : 36));
+                const int nsf1 = kind1 == 0 ? 22 : (kind1 == 1 ? 39 : (mpeg1 ? 38 : 36));
+                const int sh0 = d0.scalefac_scale() + 1, sh1 = d1.scalefac_scale() + 1;
+                const float g0 = *reinterpret_cast<const float*>(rec0 + kSfGainOff), g1 = *reinterpret_cast<const float*>(rec1 + kSfGainOff);
+                // lane = band, both channels; a second round only for the 33rd..40th band of short / mixed blocks
+                for (int b = lane; b < max(nsf0, NCH == 2 ? nsf1 : 0); b += 32) {
+                    int e0 = (int)rec0[b] << sh0, e1 = NCH == 2 ? (int)rec1[b] << sh1 : 0;
+                    float y0 = g0, y1 = g1;
+                    if (max(e0, e1) > 120) {   // rare: the loop of L3_ldexp_q2 takes more than one step
+                        for (; e0 > 120; e0 -= 120) y0 = __fmul_rn(y0, s_ldexp[120]);
+                        for (; e1 > 120; e1 -= 120) y1 = __fmul_rn(y1, s_ldexp[120]);
+                    }
+                    W.gains[0][b] = b < nsf0 ? __fmul_rn(y0, s_ldexp[e0]) : 0.0f;
+                    if (NCH == 2) W.gains[1][b] = b < nsf1 ? __fmul_rn(y1, s_ldexp[e1]) : 0.0f;
+                }
             }
             const float* const scf0 = W.gains[0];
             const float* const scf1 = W.gains[NCH - 1];
@@ -846,34 +861,36 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             const int dhi = (int)max(0ll, min(576ll, rel + (long long)countf));
             const unsigned span = (unsigned)(dhi - dlo);
 #define L3B_DELIVER(f) ((unsigned)((f) - dlo) < span)
-            // frame index in the delivered signal of this granule's first frame (pointers only dereferenced for delivered frames)
-            const long long obase = (long long)f0 - (long long)skipf;
-            T* const out = reinterpret_cast<T*>(out_base) + obase;
-            int16_t* const out16p = reinterpret_cast<int16_t*>(out_base) + obase * NCH;
+            // frame 0 of this granule in the delivered signal (only dereferenced for delivered frames); one byte pointer per
+            // granule, compile-time offsets from there: a store is a range test and a predicated STG
+            constexpr int kFrameBytes = NCH * (S16 ? 2 : 4);
+            char* const gbase = out_base + ((long long)f0 - (long long)skipf) * kFrameBytes;
             const float scale = 1.0f / 32768.0f;
             // 16-bit delivery: q = clamp(lrintf(x * 32768), -32768, 32767) of the float sample x the float path would
             // have written (the conversion SURVEY 8c defines; un-dithered, wav.d:475-700)
-            auto store = [&](int f, T v) {
+            auto store = [&](char* q, T v) {
                 const T s = V::muls(v, scale);
-                if (out16) {
+                if (S16) {
                     if (NCH == 2) {
                         const int q0 = max(-32768, min(32767, __float2int_rn(__fmul_rn(V::ch(s, 0), 32768.0f))));
                         const int q1 = max(-32768, min(32767, __float2int_rn(__fmul_rn(V::ch(s, 1), 32768.0f))));
-                        reinterpret_cast<uint32_t*>(out16p)[f] = (uint32_t)(q0 & 0xFFFF) | ((uint32_t)q1 << 16);
+                        *reinterpret_cast<uint32_t*>(q) = (uint32_t)(q0 & 0xFFFF) | ((uint32_t)q1 << 16);
                     } else {
-                        out16p[f] = (int16_t)max(-32768, min(32767, __float2int_rn(__fmul_rn(V::ch(s, 0), 32768.0f))));
+                        *reinterpret_cast<int16_t*>(q) = (int16_t)max(-32768, min(32767, __float2int_rn(__fmul_rn(V::ch(s, 0), 32768.0f))));
                     }
                 } else {
-                    out[f] = s;
+                    *reinterpret_cast<T*>(q) = s;
                 }
             };
             if (ii < 15) {
+#ifndef L3B_EXP_W_REGS
                 float w0[8], w1[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     w0[k] = s_win[(2 * k) * 32 + lane];
                     w1[k] = s_win[(2 * k + 1) * 32 + lane];
                 }
+#endif
                 // lane (par, ii) produces samples 15-ii and 17+ii of slots s = 2q + par.
                 // V[j] = D[row par + j][ j odd ? 31-ii : 1+ii ]  -- row r of D is slot r-15 ("window")
                 // Sliding window of 16 taps in registers; three slots per loop trip (the window then moves by 6
@@ -883,8 +900,11 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 const T* base_hi = D + par * kDStride + (31 - ii);
 #pragma unroll
                 for (int j = 0; j < 16; j++) Vw[j] = (j & 1) ? base_hi[j * kDStride] : base_lo[j * kDStride];
+                int fa = 32 * par + 15 - ii, fb = 32 * par + 17 + ii;   // this lane's two samples of slot `par`
+                char* pa = gbase + fa * kFrameBytes;
+                char* pb = gbase + fb * kFrameBytes;
 #pragma unroll 1
-                for (int q3 = 0; q3 < 3; q3++) {
+                for (int q3 = 0; q3 < 3; q3++, fa += 192, fb += 192, pa += 192 * kFrameBytes, pb += 192 * kFrameBytes) {
                     const T* lo = base_lo + q3 * 6 * kDStride;
                     const T* hi = base_hi + q3 * 6 * kDStride;
 #pragma unroll
@@ -912,10 +932,9 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                                 else a = V::add(a, V::mm_sub(vz, w0[k], vy, w1[k]));
                             }
                         }
-                        const int s = 2 * (3 * q3 + qq) + par;
-                        const int fa = 32 * s + 15 - ii, fb = 32 * s + 17 + ii;
-                        if (L3B_DELIVER(fa)) store(fa, a);
-                        if (L3B_DELIVER(fb)) store(fb, b);
+                        // slot s = 2 * (3 * q3 + qq) + par: samples 32 s + 15 - ii and 32 s + 17 + ii
+                        if (L3B_DELIVER(fa + 64 * qq)) store(pa + 64 * qq * kFrameBytes, a);
+                        if (L3B_DELIVER(fb + 64 * qq)) store(pb + 64 * qq * kFrameBytes, b);
                     }
 #pragma unroll
                     for (int j = 0; j < 16; j++) Vw[j] = Vw[j + 6];   // slide by three slots
@@ -937,7 +956,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 a = V::mac(a, V::sub(z[8], z[6]), 37489.0f);
                 a = V::mac(a, z[7], 75038.0f);
                 const int fa = 32 * lane, fb = 32 * lane + 16;
-                if (L3B_DELIVER(fa)) store(fa, a);
+                if (L3B_DELIVER(fa)) store(gbase + fa * kFrameBytes, a);
 #pragma unroll
                 for (int k = 0; k < 15; k += 2) z[k] = col[k * kDStride];
                 a = V::muls(z[14], 104.0f);
@@ -948,7 +967,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 a = V::mac(a, z[4], -45.0f);
                 a = V::mac(a, z[2], 146.0f);
                 a = V::mac(a, z[0], -5.0f);
-                if (L3B_DELIVER(fb)) store(fb, a);
+                if (L3B_DELIVER(fb)) store(gbase + fb * kFrameBytes, a);
             }
         }
 #undef L3B_DELIVER
@@ -993,31 +1012,33 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
     }
 }
 
-template <int NCH, int WARPS, bool FUSED, bool TAPS>
+template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16>
 static cudaError_t launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n, cudaStream_t s) {
     if (!n) return cudaSuccess;
     const size_t smem = kCtaTableBytes + (size_t)WARPS * sizeof(WarpSmem<NCH>);
     // the attribute is per device and a process may hold contexts on several: set it every time (a cheap driver call)
-    cudaError_t e = cudaFuncSetAttribute(l3_granule_kernel<NCH, WARPS, FUSED, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(l3_granule_kernel<NCH, WARPS, FUSED, TAPS, S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    l3_granule_kernel<NCH, WARPS, FUSED, TAPS><<<(n + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(p, tiles, n);
+    l3_granule_kernel<NCH, WARPS, FUSED, TAPS, S16><<<(n + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(p, tiles, n);
     return cudaGetLastError();
+}
+
+template <bool FUSED, bool TAPS, bool S16>
+static cudaError_t launch_both(const BatchParams& p, const Tile* ts, uint32_t ns, const Tile* tm, uint32_t nm, cudaStream_t s) {
+    cudaError_t e = launch_granule_t<2, kGranuleWarpsStereo, FUSED, TAPS, S16>(p, ts, ns, s);
+    if (e == cudaSuccess) e = launch_granule_t<1, kGranuleWarpsMono, FUSED, TAPS, S16>(p, tm, nm, s);
+    return e;
 }
 
 cudaError_t launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
                            uint32_t n_mono, cudaStream_t s, bool fused, bool taps) {
-    cudaError_t e;
-    if (taps) {   // float taps exist in the bit-exact mode only (they are compared bitwise)
-        e = launch_granule_t<2, kGranuleWarpsStereo, false, true>(p, tiles_stereo, n_stereo, s);
-        if (e == cudaSuccess) e = launch_granule_t<1, kGranuleWarpsMono, false, true>(p, tiles_mono, n_mono, s);
-    } else if (fused) {
-        e = launch_granule_t<2, kGranuleWarpsStereo, true, false>(p, tiles_stereo, n_stereo, s);
-        if (e == cudaSuccess) e = launch_granule_t<1, kGranuleWarpsMono, true, false>(p, tiles_mono, n_mono, s);
-    } else {
-        e = launch_granule_t<2, kGranuleWarpsStereo, false, false>(p, tiles_stereo, n_stereo, s);
-        if (e == cudaSuccess) e = launch_granule_t<1, kGranuleWarpsMono, false, false>(p, tiles_mono, n_mono, s);
-    }
-    return e;
+    const bool s16 = p.pcm16 != nullptr;
+    // float taps exist in the bit-exact float-delivery mode only (they are compared bitwise)
+    if (taps) return launch_both<false, true, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
+    if (fused) return s16 ? launch_both<true, false, true>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s)
+                          : launch_both<true, false, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
+    return s16 ? launch_both<false, false, true>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s)
+               : launch_both<false, false, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
 }
 
 }  // namespace l3b

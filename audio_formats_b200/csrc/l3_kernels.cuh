@@ -92,7 +92,7 @@ struct BatchParams {
 constexpr int kGranuleWarpsStereo = 4;   // warps (= tiles) per CTA of the granule kernel; 16 warps resident per SM.
 constexpr int kGranuleWarpsMono = 4;     // 4-warp CTAs measured best (16: 33.7 ms, 8: 28.6 ms, 4: 27.2 ms on config 2)
 
-template <int NCH, int WARPS, bool FUSED, bool TAPS>
+template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16>
 __global__ void l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles);
 
 // lane-decoupled entropy path: scalefactor kernel, big_values kernel, count1 kernel (l3_entropy.cu); returns launches

@@ -323,6 +323,7 @@ def main():
     torch.cuda.set_device(local)
     join = Join(world)
     if WORKLOAD == "config5":
+        sys.path.insert(0, str(ROOT / "tools"))
         import bench_config5
         bench_config5.run(args, rank, world, local, join)
         join.close()
