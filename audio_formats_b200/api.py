@@ -39,7 +39,7 @@ class StreamDesc(C.Structure):
     _fields_ = [("maindata_off", C.c_uint64), ("maindata_bytes", C.c_uint32), ("n_granules", C.c_uint32),
                 ("first_grch", C.c_uint64), ("pcm_off", C.c_uint64), ("pcm_skip", C.c_uint64),
                 ("pcm_count", C.c_uint64), ("nch", C.c_uint8), ("sr_idx", C.c_uint8), ("mpeg1", C.c_uint8),
-                ("reserved", C.c_uint8), ("reserved2", C.c_uint32)]
+                ("layer", C.c_uint8), ("reserved2", C.c_uint32)]
 
 
 class Taps(C.Structure):
@@ -73,7 +73,7 @@ assert C.sizeof(GrchDesc) == 16 and C.sizeof(StreamDesc) == 56, (C.sizeof(GrchDe
 GRCH_DTYPE = np.dtype([("bit_start", "<u4"), ("w1", "<u4"), ("w2", "<u4"), ("w3", "<u4")])
 STREAM_DTYPE = np.dtype([("maindata_off", "<u8"), ("maindata_bytes", "<u4"), ("n_granules", "<u4"),
                          ("first_grch", "<u8"), ("pcm_off", "<u8"), ("pcm_skip", "<u8"), ("pcm_count", "<u8"),
-                         ("nch", "u1"), ("sr_idx", "u1"), ("mpeg1", "u1"), ("reserved", "u1"), ("reserved2", "<u4")])
+                         ("nch", "u1"), ("sr_idx", "u1"), ("mpeg1", "u1"), ("layer", "u1"), ("reserved2", "<u4")])
 assert STREAM_DTYPE.itemsize == 56
 
 
@@ -327,7 +327,7 @@ class HostBatch:
             for (md, ds, d0) in cache:
                 pad = (-len(md)) % 16 + 16
                 pcm = (pcm + 3) & ~3   # 16-byte aligned PCM rows (stereo stores are 8-byte vectors)
-                sd[k] = (off, len(md), d0.n_granules, grch, pcm, d0.pcm_skip, d0.pcm_count, d0.nch, d0.sr_idx, d0.mpeg1, 0, 0)
+                sd[k] = (off, len(md), d0.n_granules, grch, pcm, d0.pcm_skip, d0.pcm_count, d0.nch, d0.sr_idx, d0.mpeg1, d0.layer, 0)
                 blobs.append(md)
                 blobs.append(np.zeros(pad, np.uint8))
                 descs.append(ds)

@@ -56,17 +56,19 @@ struct l3b_resident {
     uint8_t* d_nzc = nullptr;
     float* d_ftaps = nullptr;               // 4 x [n_grch][576] float stage snapshots (tap mode with float taps only)
     uint32_t flags = 0;
-    Tile* d_tiles[2] = {nullptr, nullptr};  // [0] stereo, [1] mono
+    float* d_l12x = nullptr;                // Layer I / II: dequantised subband samples, [n_grch][384] (only when such streams exist)
+    bool has_l12 = false;
+    Tile* d_tiles[4] = {nullptr, nullptr, nullptr, nullptr};  // [0] stereo, [1] mono (Layer III); [2] stereo, [3] mono (Layer I / II)
     HuffJob* d_jobs = nullptr;              // one per granule-channel, written by the scalefactor kernel
     uint32_t* d_group_stream = nullptr;     // stream index of granule-channel 128 k, for every k (search hint)
     uint32_t* d_counters = nullptr;         // 2 per sub-batch: item counters of the two Huffman kernels
-    uint32_t n_tiles[2] = {0, 0};
+    uint32_t n_tiles[4] = {0, 0, 0, 0};
     uint64_t n_grch = 0, pcm_floats = 0;
     uint32_t n_streams = 0;
     // capacities of the device buffers (elements), for l3b_batch_upload_reuse
     uint64_t cap_blob = 0, cap_grch = 0, cap_pcm = 0;
-    uint32_t cap_streams = 0, cap_tiles[2] = {0, 0};
-    struct Sub { uint64_t grch_lo, grch_hi; uint32_t tile_lo[2], tile_hi[2]; };
+    uint32_t cap_streams = 0, cap_tiles[4] = {0, 0, 0, 0};
+    struct Sub { uint64_t grch_lo, grch_hi; uint32_t tile_lo[4], tile_hi[4]; };
     std::vector<Sub> subs;   // the run is issued sub-batch by sub-batch (stream boundaries)
     BatchParams params{};
 };
@@ -164,6 +166,7 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** out) {
     c->t.win = reinterpret_cast<const float*>(base + o_win);
     upload_constants();
     upload_entropy_constants();
+    upload_l12_constants();
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail("constant upload", e);
     *out = c;
     return 0;
@@ -247,8 +250,8 @@ void l3b_batch_free(l3b_ctx_t* c, l3b_resident_t* r) {
     cudaFree(r->d_pcm);
     cudaFree(r->d_nzc);
     cudaFree(r->d_ftaps);
-    cudaFree(r->d_tiles[0]);
-    cudaFree(r->d_tiles[1]);
+    cudaFree(r->d_l12x);
+    for (int k = 0; k < 4; k++) cudaFree(r->d_tiles[k]);
     cudaFree(r->d_jobs);
     cudaFree(r->d_group_stream);
     cudaFree(r->d_counters);
@@ -264,23 +267,27 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     }
     if (b->n_grch >= (1ull << 31)) { c->err = "more than 2^31 granule-channels in one batch; split it into waves"; return L3B_E_PARAM; }
     // validate stream table and build the tile lists
-    std::vector<Tile> tiles[2];
+    std::vector<Tile> tiles[4];
     uint64_t expect_grch = 0;
+    bool has_l12 = false;
     for (uint32_t i = 0; i < b->n_streams; i++) {
         const l3b_stream_desc_t& s = b->streams[i];
-        if ((s.nch != 1 && s.nch != 2) || s.sr_idx > 7 || (s.maindata_off & 3) ||
+        const bool l12 = s.layer == 1 || s.layer == 2;
+        const uint64_t gran = l12 ? 384u : 576u;   // PCM frames per granule
+        if ((s.nch != 1 && s.nch != 2) || s.sr_idx > 7 || (s.maindata_off & 3) || (s.layer != 0 && s.layer != 3 && !l12) ||
             s.maindata_off + s.maindata_bytes > b->maindata_bytes || s.first_grch != expect_grch ||
-            s.pcm_off + s.pcm_count > b->pcm_floats || s.pcm_skip + s.pcm_count > (uint64_t)s.n_granules * 576u * s.nch ||
+            s.pcm_off + s.pcm_count > b->pcm_floats || s.pcm_skip + s.pcm_count > (uint64_t)s.n_granules * gran * s.nch ||
             (s.nch == 2 && ((s.pcm_off | s.pcm_skip | s.pcm_count) & 1))) {
             c->err = "stream descriptor " + std::to_string(i) + " is inconsistent";
             return L3B_E_PARAM;
         }
         expect_grch += (uint64_t)s.n_granules * s.nch;
+        has_l12 |= l12;
         if (!s.pcm_count) continue;
-        const uint64_t per = 576ull * s.nch;
+        const uint64_t per = gran * s.nch;
         uint32_t g0 = (uint32_t)(s.pcm_skip / per), g1 = (uint32_t)((s.pcm_skip + s.pcm_count + per - 1) / per);
         for (uint32_t g = g0; g < g1; g += kTileGranules)
-            tiles[s.nch == 2 ? 0 : 1].push_back({i, g, std::min<uint32_t>(kTileGranules, g1 - g)});
+            tiles[(l12 ? 2 : 0) + (s.nch == 2 ? 0 : 1)].push_back({i, g, std::min<uint32_t>(kTileGranules, g1 - g)});
     }
     if (expect_grch != b->n_grch) { c->err = "n_grch does not match the stream table"; return L3B_E_PARAM; }
     // sub-batches: cut at stream boundaries into up to kMaxSubs pieces of similar size (>= 64 K granule-channels each)
@@ -289,18 +296,18 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
         int want = 1;  // measured on B200: overlapping the two kernels through sub-batches does not pay (39.2 ms for 1, 39.5 for 4, 41.3 for 16)
         if (getenv("L3B_SUBBATCHES")) want = std::max(1, std::min((int)l3b_ctx::kMaxSubs, atoi(getenv("L3B_SUBBATCHES"))));
         uint64_t per = (b->n_grch + want - 1) / want, lo = 0;
-        uint32_t t_at[2] = {0, 0};
-        l3b_resident::Sub cur{0, 0, {0, 0}, {0, 0}};
+        uint32_t t_at[4] = {0, 0, 0, 0};
+        l3b_resident::Sub cur{0, 0, {0, 0, 0, 0}, {0, 0, 0, 0}};
         for (uint32_t i = 0; i < b->n_streams; i++) {
             const l3b_stream_desc_t& s = b->streams[i];
             uint64_t hi = s.first_grch + (uint64_t)s.n_granules * s.nch;
-            for (int k = 0; k < 2; k++)
+            for (int k = 0; k < 4; k++)
                 while (t_at[k] < tiles[k].size() && tiles[k][t_at[k]].stream == i) t_at[k]++;
             if (hi - lo >= per || i + 1 == b->n_streams) {
                 cur.grch_lo = lo; cur.grch_hi = hi;
-                cur.tile_hi[0] = t_at[0]; cur.tile_hi[1] = t_at[1];
+                for (int k = 0; k < 4; k++) cur.tile_hi[k] = t_at[k];
                 subs.push_back(cur);
-                cur.tile_lo[0] = t_at[0]; cur.tile_lo[1] = t_at[1];
+                for (int k = 0; k < 4; k++) cur.tile_lo[k] = t_at[k];
                 lo = hi;
             }
         }
@@ -324,9 +331,10 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     // (re)allocate what is too small; recycled workspaces get 12.5 % headroom so that they settle quickly
     auto grow = [&](uint64_t need) { return reuse ? need + need / 8 + 64 : need; };
     bool stale = false;  // a buffer in use by queued work is about to be freed
-    if (b->maindata_bytes + 64 > r->cap_blob || b->n_grch > r->cap_grch || b->pcm_floats > r->cap_pcm ||
-        b->n_streams > r->cap_streams || tiles[0].size() > r->cap_tiles[0] || tiles[1].size() > r->cap_tiles[1])
+    if (b->maindata_bytes + 64 > r->cap_blob || b->n_grch > r->cap_grch || b->pcm_floats > r->cap_pcm || b->n_streams > r->cap_streams)
         stale = true;
+    for (int k = 0; k < 4; k++)
+        if (tiles[k].size() > r->cap_tiles[k]) stale = true;
     const uint32_t flags = b->flags;
     const size_t pcm_elem = (flags & L3B_OUT_S16) ? sizeof(int16_t) : sizeof(float);
     const bool pcm_kind_changed = ((r->flags ^ flags) & L3B_OUT_S16) != 0;
@@ -339,7 +347,8 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     }
     if (b->n_grch > r->cap_grch || !r->d_grch) {
         cudaFree(r->d_grch); cudaFree(r->d_is); cudaFree(r->d_sf); cudaFree(r->d_jobs); cudaFree(r->d_group_stream); cudaFree(r->d_nzc);
-        cudaFree(r->d_ftaps);
+        cudaFree(r->d_ftaps); cudaFree(r->d_l12x);
+        r->d_l12x = nullptr;
         r->d_grch = nullptr; r->d_is = nullptr; r->d_sf = nullptr; r->d_jobs = nullptr; r->d_group_stream = nullptr; r->d_nzc = nullptr;
         r->d_ftaps = nullptr;
         r->cap_grch = std::max<uint64_t>(1, grow(b->n_grch));
@@ -350,6 +359,8 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
         CU_TRY_R(cudaMalloc(&r->d_group_stream, (r->cap_grch / 128 + 2) * sizeof(uint32_t)));
         CU_TRY_R(cudaMalloc(&r->d_nzc, r->cap_grch + 16));
     }
+    r->has_l12 = has_l12;
+    if (has_l12 && !r->d_l12x) CU_TRY_R(cudaMalloc(&r->d_l12x, r->cap_grch * 384 * sizeof(float)));
     const bool want_ftaps = b->taps && (b->taps->xr || b->taps->st || b->taps->im || b->taps->dct);
     if (want_ftaps && (flags & (L3B_OUT_S16 | L3B_MATH_FUSED))) {
         c->err = "float taps exist in the bit-exact float-delivery mode only";
@@ -371,7 +382,7 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
         r->cap_streams = (uint32_t)grow(b->n_streams);
         CU_TRY_R(cudaMalloc(&r->d_streams, r->cap_streams * sizeof(l3b_stream_desc_t)));
     }
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 4; k++) {
         r->n_tiles[k] = (uint32_t)tiles[k].size();
         if (tiles[k].size() > r->cap_tiles[k]) {
             cudaFree(r->d_tiles[k]); r->d_tiles[k] = nullptr;
@@ -387,7 +398,7 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     if (b->maindata_bytes) CU_TRY_R(cudaMemcpyAsync(r->d_blob, b->maindata, b->maindata_bytes, cudaMemcpyHostToDevice, c->stream));
     if (b->n_grch) CU_TRY_R(cudaMemcpyAsync(r->d_grch, b->grch, b->n_grch * sizeof(l3b_grch_desc_t), cudaMemcpyHostToDevice, c->stream));
     CU_TRY_R(cudaMemcpyAsync(r->d_streams, b->streams, b->n_streams * sizeof(l3b_stream_desc_t), cudaMemcpyHostToDevice, c->stream));
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < 4; k++)
         if (r->n_tiles[k])
             CU_TRY_R(cudaMemcpyAsync(r->d_tiles[k], tiles[k].data(), tiles[k].size() * sizeof(Tile), cudaMemcpyHostToDevice, c->stream));
     std::vector<uint32_t> group_stream((size_t)(b->n_grch / 128 + 1));
@@ -413,6 +424,7 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     p.pcm = (flags & L3B_OUT_S16) ? nullptr : r->d_pcm;
     p.pcm16 = (flags & L3B_OUT_S16) ? reinterpret_cast<int16_t*>(r->d_pcm) : nullptr;
     p.nzc = r->d_nzc;
+    p.l12_x = has_l12 ? r->d_l12x : nullptr;
     p.tap_xr = p.tap_st = p.tap_im = p.tap_dct = nullptr;
     if (want_ftaps) {
         p.tap_xr = r->d_ftaps;
@@ -468,6 +480,10 @@ int l3b_batch_run(l3b_ctx_t* c, l3b_resident_t* r) {
         p.grch_lo = sb.grch_lo;
         p.grch_hi = sb.grch_hi;
         launches += launch_entropy_v4(p, i, c->sms, A);
+        if (r->has_l12) {   // Layer I / II streams of this sub-batch: unallocated subbands stay +0 (the reference's memset grbuf)
+            CU_TRY(c, cudaMemsetAsync(r->d_l12x + sb.grch_lo * 384, 0, (sb.grch_hi - sb.grch_lo) * 384 * sizeof(float), A));
+            launches += launch_l12_parse(p, A);
+        }
         cudaEvent_t* se = ev + 3 + 3 * i;
         CU_TRY(c, cudaEventRecord(se[0], A));
         CU_TRY(c, cudaStreamWaitEvent(B, se[0], 0));   // granule kernels of sub-batch i wait for its spectra only
@@ -476,6 +492,12 @@ int l3b_batch_run(l3b_ctx_t* c, l3b_resident_t* r) {
         CU_TRY(c, launch_granule(p, r->d_tiles[0] + sb.tile_lo[0], n2, r->d_tiles[1] + sb.tile_lo[1], n1, B,
                                  (r->flags & L3B_MATH_FUSED) != 0, p.tap_xr != nullptr));
         launches += (n2 > 0) + (n1 > 0);
+        if (r->has_l12) {
+            const uint32_t m2 = sb.tile_hi[2] - sb.tile_lo[2], m1 = sb.tile_hi[3] - sb.tile_lo[3];
+            CU_TRY(c, launch_granule_l12(p, r->d_tiles[2] + sb.tile_lo[2], m2, r->d_tiles[3] + sb.tile_lo[3], m1, B,
+                                         (r->flags & L3B_MATH_FUSED) != 0));
+            launches += (m2 > 0) + (m1 > 0);
+        }
         CU_TRY(c, cudaEventRecord(se[2], B));
     }
     CU_TRY(c, cudaEventRecord(ev[1], A));

@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
     ScfReader br;
     br.words = reinterpret_cast<const uint32_t*>(p.blob + S->maindata_off);
     br.nwords = (S->maindata_bytes >> 2) + 4;  // the batch blob keeps >= 16 zero bytes after each stream
-    const Desc d = load_desc(p.grch + gi);
+    Desc d = load_desc(p.grch + gi);
+    if (S->layer == 1 || S->layer == 2) d.w1 = d.w2 = d.w3 = 0;   // a Layer I / II granule (l12_parse_kernel's): an empty Huffman job
     br.open(d.bit_start);
 
     // ---------------- scalefactors (minimp3.d:613-644, 659-712) ----------------

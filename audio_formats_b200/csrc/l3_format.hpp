@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "../../include/l3b200.h"
+#include "l12_tables.h"
 #include "l3_tables_gen.h"
 
 namespace l3b {
@@ -130,6 +131,72 @@ struct BitReader {
         return v;
     }
 };
+
+// ---- Layer I / II (minimp3.d:284-470): what the host needs -- does the frame decode, i.e. does the bit position stay inside
+// the frame after each of the three L12_dequantize_granule calls (minimp3.d:1571-1575)?  The scale info is parsed exactly like
+// the reference parses it, including its reading of a 2-bit scfsi field for EVERY band-channel entry of a Layer II frame
+// (minimp3.d:417-421 evaluates get_bits before testing the allocation; ISO 11172-3 and the upstream C read it only for
+// allocated entries).  The samples themselves are only counted here; the device parser decodes them.
+inline void l12_alloc_table(const uint8_t* hdr, const uint8_t (**rows)[3], int* total_bands, int* stereo_bands) {
+    const Hdr H(hdr);
+    const int mode = (hdr[3] >> 6) & 3;   // 3 = mono, 1 = joint stereo
+    int sb = mode == 3 ? 0 : (mode == 1 ? (((hdr[3] >> 4) & 3) << 2) + 4 : 32), nbands;
+    if (H.layer1()) {
+        *rows = L12_ALLOC_L1; nbands = 32;
+    } else if (!H.mpeg1()) {
+        *rows = L12_ALLOC_L2M2; nbands = 30;
+    } else {
+        unsigned kbps = H.bitrate_kbps() >> (mode != 3 ? 1 : 0);
+        if (!kbps) kbps = 192;   // free format
+        *rows = L12_ALLOC_L2M1; nbands = 27;
+        if (kbps < 56) { *rows = L12_ALLOC_L2M1_LOWRATE; nbands = H.sr_bits() == 2 ? 12 : 8; }
+        else if (kbps >= 96 && H.sr_bits() != 1) nbands = 30;
+    }
+    *total_bands = nbands;
+    *stereo_bands = sb < nbands ? sb : nbands;
+}
+
+inline bool l12_frame_fits(const uint8_t* hdr, int frame_size) {
+    BitReader bs(hdr + kHdrSize, frame_size - kHdrSize);
+    if (Hdr(hdr).has_crc()) bs.get(16);
+    const uint8_t (*rows)[3];
+    int total, stereo;
+    l12_alloc_table(hdr, &rows, &total, &stereo);
+    const bool l1 = Hdr(hdr).layer1();
+    uint8_t bitalloc[64], scfcod[64];
+    int k = 0, ba_bits = 0;
+    const uint8_t* tab = L12_BITALLOC_CODE_TAB;
+    for (int i = 0; i < total; i++) {
+        if (i == k) { k += (*rows)[2]; ba_bits = (*rows)[1]; tab = L12_BITALLOC_CODE_TAB + (*rows)[0]; rows++; }
+        uint8_t ba = tab[bs.get(ba_bits)];
+        bitalloc[2 * i] = ba;
+        if (i < stereo) ba = tab[bs.get(ba_bits)];
+        bitalloc[2 * i + 1] = stereo ? ba : 0;
+    }
+    for (int i = 0; i < 2 * total; i++) {
+        const uint8_t temp = l1 ? 2 : (uint8_t)bs.get(2);
+        scfcod[i] = bitalloc[i] ? temp : 6;
+    }
+    for (int i = 0; i < 2 * total; i++) {
+        const int mask = bitalloc[i] ? 4 + ((19 >> scfcod[i]) & 3) : 0;
+        for (int m = 4; m; m >>= 1)
+            if (mask & m) bs.get(6);
+    }
+    for (int i = stereo; i < total; i++) bitalloc[2 * i + 1] = 0;
+    const int group = l1 ? 1 : 3;
+    int per_call = 0;
+    for (int i = 0; i < 2 * total; i++) {
+        const int ba = bitalloc[i];
+        if (!ba) continue;
+        const int mod = (2 << (ba - 17)) + 1;
+        per_call += 4 * (ba < 17 ? group * ba : mod + 2 - (mod >> 3));
+    }
+    for (int igr = 0; igr < 3; igr++) {
+        bs.pos += per_call;
+        if (bs.pos > bs.limit) return false;
+    }
+    return true;
+}
 
 // ---- Layer III side info (minimp3.d:189-196, 487-611) ---------------------------------------------
 struct GranuleInfo {

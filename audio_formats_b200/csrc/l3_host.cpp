@@ -73,10 +73,32 @@ int FrameWalker::step(const uint8_t* mp3, int mp3_bytes, FrameInfo* info, Progra
     if (H.has_crc()) bs.get(16);  // skipped, never verified (minimp3.d:1533-1536)
 
     if (info->layer != 3) {
-        // Layer I/II is outside this path: treated as undecodable, state dropped.
-        unsupported_layer = true;
-        init();
-        return 0;
+        // Layer I / II (minimp3.d:1557-1579): no reservoir, one frame = one (Layer I) or three (Layer II) "granules" of 12 slots
+        // x 32 subbands.  The frame is dropped, and the decoder state with it, when its bits run past its end.
+        if (!l12_frame_fits(hdr, frame_size)) {
+            init();
+            return 0;
+        }
+        const int nch = info->channels, parts = H.layer1() ? 1 : 3;
+        if (prog) {
+            const uint64_t start_bit = (uint64_t)prog->blob.size() * 8u;   // of the frame body (what follows the header)
+            for (int part = 0; part < parts; part++) {
+                for (int ch = 0; ch < nch; ch++) {
+                    l3b_grch_desc_t d;
+                    d.bit_start = (uint32_t)std::min<uint64_t>(start_bit, 0xFFFFFFFFull);
+                    d.w1 = (uint32_t)hdr[1] | ((uint32_t)hdr[2] << 8) | ((uint32_t)hdr[3] << 16);   // version / layer / crc, rate, mode
+                    d.w2 = (uint32_t)part | (part ? 0x80000000u : 0u);
+                    d.w3 = pending_reset ? 0x80000000u : 0u;
+                    prog->descs.push_back(d);
+                }
+                pending_reset = false;
+                prog->granules++;
+            }
+            prog->blob.insert(prog->blob.end(), hdr + kHdrSize, hdr + frame_size);
+        } else {
+            pending_reset = false;
+        }
+        return (int)H.frame_samples();
     }
     GranuleInfo gr[4];
     int mdb = parse_side_info(bs, gr, hdr);
@@ -352,7 +374,8 @@ int scan_stream(const uint8_t* data, size_t size, ScanResult* out) {
     OpenInfo& oi = out->open;
     int rc = open_index(data, size, &oi);
     if (rc) return rc;
-    if (oi.info.layer != 3) return oi.info.layer ? L3B_E_UNSUPPORTED : L3B_E_USER;
+    if (!oi.info.layer) return L3B_E_USER;
+    out->layer = oi.info.layer;
     out->channels = oi.info.channels;
     out->hz = oi.info.hz;
     out->length_frames = oi.info.channels ? oi.samples / oi.info.channels : 0;
@@ -390,7 +413,6 @@ int scan_stream(const uint8_t* data, size_t size, ScanResult* out) {
     }
     out->pcm_skip = skipped;
     out->pcm_count = cur;
-    if (rd.walker.unsupported_layer && !out->prog.granules) return L3B_E_UNSUPPORTED;
     return 0;
 }
 
@@ -438,6 +460,7 @@ void l3b_scan_fill_stream_desc(const l3b_scan_t* s, l3b_stream_desc_t* d) {
     d->nch = (uint8_t)s->r.channels;
     d->sr_idx = (uint8_t)s->r.sr_idx;
     d->mpeg1 = (uint8_t)s->r.mpeg1;
+    d->layer = (uint8_t)(s->r.layer == 3 ? 0 : s->r.layer);
 }
 
 }  // extern "C"

@@ -42,7 +42,6 @@ class FrameWalker {
     int free_format_bytes = 0;
     int reserv = 0;             // valid reservoir bytes == the last `reserv` bytes of prog->blob
     bool pending_reset = true;  // overlap/qmf/reservoir were zeroed since the last emitted granule
-    bool unsupported_layer = false;
 
     void init() { header[0] = 0; }  // mp3dec_init, minimp3.d:1487
 
@@ -103,7 +102,7 @@ class Reader {
 struct ScanResult {
     OpenInfo open;
     Program prog;
-    int channels = 0, hz = 0, sr_idx = 0, mpeg1 = 0;
+    int channels = 0, hz = 0, sr_idx = 0, mpeg1 = 0, layer = 0;
     uint64_t length_frames = 0;
     uint64_t pcm_skip = 0, pcm_count = 0;  // delivered window inside the decoded signal (interleaved samples)
     int last_error = 0;

@@ -364,10 +364,13 @@ __device__ __noinline__ void imdct_split(float* x, float* ovl, float* y, bool sh
 
 constexpr int kCtaTableBytes = 1040 + 496 + 2048;   // s_pow43 (257 floats + pad) | s_ldexp (121 floats + pad) | s_win (16 x 32 floats)
 
-template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16>
+// L12: the Layer I / II instance -- a granule is 12 slots x 32 subbands whose samples arrive dequantised and scaled from
+// l12_parse_kernel (p.l12_x); only the synthesis half of the pipeline runs (minimp3.d:1567 calls mp3d_synth_granule with 12).
+template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16, bool L12>
 __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
     typedef VT<NCH, FUSED> V;
     typedef typename V::T T;
+    constexpr int NS = L12 ? 12 : 18;   // time slots per granule
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float* s_pow43 = reinterpret_cast<float*>(smem_raw);          // 257 signed entries (+pad), shared by the CTA
     float* s_ldexp = reinterpret_cast<float*>(smem_raw + 1040);   // one step of L3_ldexp_q2: g_expfrac[e & 3] * 2^(30 - (e >> 2)), e <= 120
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
     // transmit keeps what granule 0 left there.  A halo that starts on granule 1 of an intensity-stereo frame therefore
     // starts one granule earlier, so that granule 0's intensity pass has run (it only matters when the two channels use
     // different block types, but the extra granule is cheap: it happens once per tile of a stream with an odd delay).
-    if (NCH == 2 && have_tile && start > 0 && start < (int)tile.g0) {
+    if (!L12 && NCH == 2 && have_tile && start > 0 && start < (int)tile.g0) {
         const Desc ds = load_desc(p.grch + S.first_grch + (uint64_t)start * NCH);
         if (ds.second_granule() && !ds.reset_before() && (ds.hdr_bits() & 1)) start--;
     }
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
         n1 = NCH == 2 ? __ldg(q + 1) : 0u;
     };
     uint32_t nzn0 = 0, nzn1 = 0;   // lane 0: nz_chunks of the NEXT granule
-    if (lane == 0 && n_iter > 0) {
+    if (!L12 && lane == 0 && n_iter > 0) {
         load_nz(start, nzn0, nzn1);
         prefetch(start, nzn0, nzn1);
     }
@@ -464,14 +467,33 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
     for (int it = 0; it < kMaxIter; it++) {
         const bool act = it < n_iter;
         const int g = start + it;
-        const int mode = g >= (int)tile.g0 ? 2 : (g == (int)tile.g0 - 1 ? 1 : 0);
+        // 2: a granule of the tile; 1: halo granule whose DCT outputs are history for the window; 0: halo granule that only
+        // contributes IMDCT overlap.  Layer I / II: 12 slots per granule, so the 15 history slots span both halo granules.
+        const int mode = g >= (int)tile.g0 ? 2 : ((L12 || g == (int)tile.g0 - 1) ? 1 : 0);
         const uint64_t di = S.first_grch + (uint64_t)g * NCH;
         Desc d0, d1;
         d0.bit_start = d0.w1 = d0.w2 = d0.w3 = 0;
         d1 = d0;
         int kind0 = 0, kind1 = 0, hb = 0;
         bool ms_frame = false, istereo = false;
-        if (act) {
+        if (L12) {
+            if (act) {
+                const Desc dd = load_desc(p.grch + di);
+                if (dd.reset_before() && it != 0)
+                    for (int i = lane; i < 15 * kDStride; i += 32) D[i] = V::zero();
+                // lane = subband: its 12 samples of both channels, into the padded layout the DCT reads
+                const float4* x0 = reinterpret_cast<const float4*>(p.l12_x + di * 384 + lane * 12);
+                const float4* x1 = reinterpret_cast<const float4*>(p.l12_x + (di + NCH - 1) * 384 + lane * 12);
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const float4 a = __ldg(x0 + q), b = NCH == 2 ? __ldg(x1 + q) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    xr[lane * 19 + 4 * q + 0] = V::pack(a.x, b.x);
+                    xr[lane * 19 + 4 * q + 1] = V::pack(a.y, b.y);
+                    xr[lane * 19 + 4 * q + 2] = V::pack(a.z, b.z);
+                    xr[lane * 19 + 4 * q + 3] = V::pack(a.w, b.w);
+                }
+            }
+        } else if (act) {
             if (lane == 0 && it + 1 < n_iter) load_nz(g + 1, nzn0, nzn1);   // used after requantisation
             mbar_wait(&W.mbar, it & 1);
             {
@@ -704,7 +726,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
         L3B_PHASE_SYNC();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
 
         // ---------------- reorder + antialias + IMDCT + frequency inversion (minimp3.d:1215-1229) ----------
-        if (act) {
+        if (!L12 && act) {
             T x[18], y[18];
             const int bt0 = d0.block_type(), bt1 = d1.block_type();
             const int nlb0 = kind0 == 2 ? n_long_bands_mixed : 0, nlb1 = kind1 == 2 ? n_long_bands_mixed : 0;
@@ -788,7 +810,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
         L3B_PHASE_SYNC();
 
         // ---------------- DCT-32 matrixing across bands, one time slot per lane (minimp3.d:1232-1298) -------
-        if (act && mode >= 1 && lane < 18) {
+        if (act && mode >= 1 && lane < NS) {
             T t[4][8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -805,7 +827,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 t[2][i] = V::add(t3, t2);
                 t[3][i] = V::muls(V::sub(t3, t2), c_sec[3 * i + 2]);
             }
-            __syncwarp(0x3FFFFu);  // all 18 slots have read their column: the buffer may now take the output rows
+            __syncwarp((1u << NS) - 1u);  // all slots have read their column: the buffer may now take the output rows
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 T x0 = t[r][0], x1 = t[r][1], x2 = t[r][2], x3 = t[r][3], x4 = t[r][4], x5 = t[r][5], x6 = t[r][6], x7 = t[r][7], xt;
@@ -845,7 +867,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             out[30] = t[1][7];
             out[31] = t[3][7];
             if (TAPS && mode == 2) {   // the reference's in-place layout: output j of slot k at grbuf[j*18 + k]
-                __syncwarp(0x3FFFFu);
+                __syncwarp((1u << NS) - 1u);
                 for (int j = 0; j < 32; j++)
                     for (int c = 0; c < NCH; c++) p.tap_dct[(di + c) * 576 + j * 18 + lane] = V::ch(out[j], c);
             }
@@ -854,11 +876,12 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
 
         // ---------------- 512-tap window (minimp3.d:1305-1406) ----------------
         if (act && mode == 2) {
-            const uint64_t f0 = (uint64_t)g * 576u;   // first frame of this granule in the decoded signal
-            // samples [lo, hi) of this granule are delivered (all 576 except at the edges of the stream's PCM range)
+            constexpr long long kGranFrames = 32 * NS;   // 576 (Layer III) / 384 (Layer I / II)
+            const uint64_t f0 = (uint64_t)g * (uint64_t)kGranFrames;   // first frame of this granule in the decoded signal
+            // samples [lo, hi) of this granule are delivered (all of them except at the edges of the stream's PCM range)
             const long long rel = (long long)skipf - (long long)f0;
-            const int dlo = (int)max(0ll, min(576ll, rel));
-            const int dhi = (int)max(0ll, min(576ll, rel + (long long)countf));
+            const int dlo = (int)max(0ll, min(kGranFrames, rel));
+            const int dhi = (int)max(0ll, min(kGranFrames, rel + (long long)countf));
             const unsigned span = (unsigned)(dhi - dlo);
 #define L3B_DELIVER(f) ((unsigned)((f) - dlo) < span)
             // frame 0 of this granule in the delivered signal (only dereferenced for delivered frames); one byte pointer per
@@ -904,7 +927,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 char* pa = gbase + fa * kFrameBytes;
                 char* pb = gbase + fb * kFrameBytes;
 #pragma unroll 1
-                for (int q3 = 0; q3 < 3; q3++, fa += 192, fb += 192, pa += 192 * kFrameBytes, pb += 192 * kFrameBytes) {
+                for (int q3 = 0; q3 < NS / 6; q3++, fa += 192, fb += 192, pa += 192 * kFrameBytes, pb += 192 * kFrameBytes) {
                     const T* lo = base_lo + q3 * 6 * kDStride;
                     const T* hi = base_hi + q3 * 6 * kDStride;
 #pragma unroll
@@ -941,7 +964,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 }
             }
             // samples 0 and 16 of every slot (mp3d_synth_pair), one slot per lane
-            if (lane < 18) {
+            if (lane < NS) {
                 const T* col = D + lane * kDStride;   // row lane + k is slot lane - 15 + k
                 T z[15];
 #pragma unroll
@@ -977,9 +1000,9 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             if (NCH == 2) {
                 // 15 x 33 float2 = 495 elements moved down by 18 rows.  D is 8 bytes past a 16-byte boundary, and so is
                 // D + 18 rows: element 0 goes alone, elements 1..494 as 247 16-byte vectors.
-                const float4* src = reinterpret_cast<const float4*>(D + 18 * kDStride + 1);
+                const float4* src = reinterpret_cast<const float4*>(D + NS * kDStride + 1);
                 float4* dst = reinterpret_cast<float4*>(D + 1);
-                const T first = D[18 * kDStride];
+                const T first = D[NS * kDStride];
                 float4 tmp[8];
 #pragma unroll
                 for (int m = 0; m < 8; m++) {
@@ -998,7 +1021,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
 #pragma unroll
                 for (int m = 0; m < 16; m++) {
                     const int e = lane + 32 * m;
-                    if (e < 15 * kDStride) tmp[m] = D[18 * kDStride + e];
+                    if (e < 15 * kDStride) tmp[m] = D[NS * kDStride + e];
                 }
                 __syncwarp();
 #pragma unroll
@@ -1012,21 +1035,21 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
     }
 }
 
-template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16>
+template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16, bool L12>
 static cudaError_t launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n, cudaStream_t s) {
     if (!n) return cudaSuccess;
     const size_t smem = kCtaTableBytes + (size_t)WARPS * sizeof(WarpSmem<NCH>);
     // the attribute is per device and a process may hold contexts on several: set it every time (a cheap driver call)
-    cudaError_t e = cudaFuncSetAttribute(l3_granule_kernel<NCH, WARPS, FUSED, TAPS, S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(l3_granule_kernel<NCH, WARPS, FUSED, TAPS, S16, L12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    l3_granule_kernel<NCH, WARPS, FUSED, TAPS, S16><<<(n + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(p, tiles, n);
+    l3_granule_kernel<NCH, WARPS, FUSED, TAPS, S16, L12><<<(n + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(p, tiles, n);
     return cudaGetLastError();
 }
 
-template <bool FUSED, bool TAPS, bool S16>
+template <bool FUSED, bool TAPS, bool S16, bool L12>
 static cudaError_t launch_both(const BatchParams& p, const Tile* ts, uint32_t ns, const Tile* tm, uint32_t nm, cudaStream_t s) {
-    cudaError_t e = launch_granule_t<2, kGranuleWarpsStereo, FUSED, TAPS, S16>(p, ts, ns, s);
-    if (e == cudaSuccess) e = launch_granule_t<1, kGranuleWarpsMono, FUSED, TAPS, S16>(p, tm, nm, s);
+    cudaError_t e = launch_granule_t<2, kGranuleWarpsStereo, FUSED, TAPS, S16, L12>(p, ts, ns, s);
+    if (e == cudaSuccess) e = launch_granule_t<1, kGranuleWarpsMono, FUSED, TAPS, S16, L12>(p, tm, nm, s);
     return e;
 }
 
@@ -1034,11 +1057,20 @@ cudaError_t launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint3
                            uint32_t n_mono, cudaStream_t s, bool fused, bool taps) {
     const bool s16 = p.pcm16 != nullptr;
     // float taps exist in the bit-exact float-delivery mode only (they are compared bitwise)
-    if (taps) return launch_both<false, true, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
-    if (fused) return s16 ? launch_both<true, false, true>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s)
-                          : launch_both<true, false, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
-    return s16 ? launch_both<false, false, true>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s)
-               : launch_both<false, false, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
+    if (taps) return launch_both<false, true, false, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
+    if (fused) return s16 ? launch_both<true, false, true, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s)
+                          : launch_both<true, false, false, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
+    return s16 ? launch_both<false, false, true, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s)
+               : launch_both<false, false, false, false>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
+}
+
+cudaError_t launch_granule_l12(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
+                               uint32_t n_mono, cudaStream_t s, bool fused) {
+    const bool s16 = p.pcm16 != nullptr;
+    if (fused) return s16 ? launch_both<true, false, true, true>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s)
+                          : launch_both<true, false, false, true>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
+    return s16 ? launch_both<false, false, true, true>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s)
+               : launch_both<false, false, false, true>(p, tiles_stereo, n_stereo, tiles_mono, n_mono, s);
 }
 
 }  // namespace l3b

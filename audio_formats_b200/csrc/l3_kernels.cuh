@@ -80,6 +80,8 @@ struct BatchParams {
     uint8_t* nzc;    // [n_grch] nz_chunks again, packed: read a granule ahead by the granule kernel to size its TMA copies
     float* pcm;      // float delivery (NULL when pcm16 is set)
     int16_t* pcm16;  // 16-bit delivery: q = clamp(lrintf(x * 32768)) of the float sample, same element offsets
+    float* l12_x;    // [n_grch][384] Layer I / II: dequantised, scaled subband samples [band 32][slot 12] per granule-channel
+                     //   (NULL when the batch holds no Layer I / II stream); zeroed before every run
     float *tap_xr, *tap_st, *tap_im, *tap_dct;   // [n_grch][576] float stage snapshots (test taps; TAPS kernels only)
     uint64_t grch_lo, grch_hi;  // granule-channel range the entropy kernels cover in this launch
     int zero_fill;   // the count1 kernel zero-fills the chunks it does not reach (tap mode)
@@ -92,7 +94,7 @@ struct BatchParams {
 constexpr int kGranuleWarpsStereo = 4;   // warps (= tiles) per CTA of the granule kernel; 16 warps resident per SM.
 constexpr int kGranuleWarpsMono = 4;     // 4-warp CTAs measured best (16: 33.7 ms, 8: 28.6 ms, 4: 27.2 ms on config 2)
 
-template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16>
+template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16, bool L12>
 __global__ void l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles);
 
 // lane-decoupled entropy path: scalefactor kernel, big_values kernel, count1 kernel (l3_entropy.cu); returns launches
@@ -100,7 +102,13 @@ int launch_entropy_v4(const BatchParams& p, int sub, int sms, cudaStream_t s);
 // fused: tolerance-mode arithmetic (hand-contracted FFMA2) instead of the bit-exact one; taps: float stage snapshots
 cudaError_t launch_granule(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
                            uint32_t n_mono, cudaStream_t s, bool fused, bool taps);
+// Layer I / II (l12_kernels.cu): one thread per 12-slot granule parses its share of the frame into p.l12_x; returns launches
+int launch_l12_parse(const BatchParams& p, cudaStream_t s);
+// the L12 instances of the granule kernel: synthesis only, 12 slots per granule
+cudaError_t launch_granule_l12(const BatchParams& p, const Tile* tiles_stereo, uint32_t n_stereo, const Tile* tiles_mono,
+                               uint32_t n_mono, cudaStream_t s, bool fused);
 void upload_constants();
 void upload_entropy_constants();
+void upload_l12_constants();
 
 }  // namespace l3b

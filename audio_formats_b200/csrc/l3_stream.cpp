@@ -25,7 +25,8 @@ struct l3b_stream {
     l3b_ctx_t* ctx = nullptr;
     std::vector<uint8_t> data;
     OpenInfo oi;
-    int channels = 0, hz = 0, sr_idx = 0, mpeg1 = 0;
+    int channels = 0, hz = 0, sr_idx = 0, mpeg1 = 0, layer = 3;
+    uint32_t gran = 576;   // PCM frames per granule: 576 (Layer III), 384 (Layer I / II: 12 slots x 32 subbands)
     int64_t length_frames = 0;
     Reader* reader = nullptr;
     // mp3dec_ex_t sample bookkeeping (minimp3_ex.d:79-86)
@@ -68,7 +69,7 @@ static int decode_pending(l3b_stream* s) {
     const int nch = s->channels;
     // slice: two granules of halo, widened to a frame boundary so granule 1 can see granule 0's scalefactors
     uint32_t seg0 = g_new0 >= 2 ? g_new0 - 2 : 0;
-    if (seg0 > 0 && (s->prog.descs[(size_t)seg0 * nch].w2 >> 31)) seg0--;
+    if (s->layer == 3 && seg0 > 0 && (s->prog.descs[(size_t)seg0 * nch].w2 >> 31)) seg0--;
     std::vector<l3b_grch_desc_t> descs(s->prog.descs.begin() + (size_t)seg0 * nch, s->prog.descs.begin() + (size_t)g_new1 * nch);
     uint32_t min_bit = 0xFFFFFFFFu;
     for (auto& d : descs) min_bit = std::min(min_bit, d.bit_start);
@@ -84,16 +85,17 @@ static int decode_pending(l3b_stream* s) {
     sd.n_granules = g_new1 - seg0;
     sd.first_grch = 0;
     sd.pcm_off = 0;
-    sd.pcm_skip = (uint64_t)(g_new0 - seg0) * 576u * nch;
-    sd.pcm_count = (uint64_t)(g_new1 - g_new0) * 576u * nch;
+    sd.pcm_skip = (uint64_t)(g_new0 - seg0) * s->gran * nch;
+    sd.pcm_count = (uint64_t)(g_new1 - g_new0) * s->gran * nch;
     sd.nch = (uint8_t)nch;
     sd.sr_idx = (uint8_t)s->sr_idx;
     sd.mpeg1 = (uint8_t)s->mpeg1;
+    sd.layer = (uint8_t)(s->layer == 3 ? 0 : s->layer);
 
     // drop cached granules that precede the frame still being consumed
     if (s->head_granule > s->cache_g0) {
         uint32_t drop = std::min(s->head_granule, s->cache_g1) - s->cache_g0;
-        s->cache.erase(s->cache.begin(), s->cache.begin() + (size_t)drop * 576u * nch);
+        s->cache.erase(s->cache.begin(), s->cache.begin() + (size_t)drop * s->gran * nch);
         s->cache_g0 += drop;
     }
     const size_t old = s->cache.size();
@@ -130,7 +132,7 @@ static int refill(l3b_stream* s) {
 }
 
 static const float* frame_pcm(const l3b_stream* s, uint32_t first_granule) {
-    return s->cache.data() + (size_t)(first_granule - s->cache_g0) * 576u * s->channels;
+    return s->cache.data() + (size_t)(first_granule - s->cache_g0) * s->gran * s->channels;
 }
 
 // mp3dec_ex_read (minimp3_ex.d:787-888), callback-I/O arm
@@ -294,10 +296,12 @@ static int stream_open(l3b_ctx_t* ctx, std::vector<uint8_t>&& bytes, l3b_stream_
     // stream.d:1706-1749: detect with a 32 KiB scratch, then open with MP3D_SEEK_TO_SAMPLE
     int rc = detect_mp3(data, size);
     if (!rc) rc = open_index(data, size, &s->oi);
-    if (!rc && s->oi.info.layer != 3) rc = s->oi.info.layer ? L3B_E_UNSUPPORTED : L3B_E_USER;
+    if (!rc && !s->oi.info.layer) rc = L3B_E_USER;
     if (rc) { delete s; return rc; }
     s->channels = s->oi.info.channels;
     s->hz = s->oi.info.hz;
+    s->layer = s->oi.info.layer;
+    s->gran = s->layer == 3 ? 576u : 384u;
     s->length_frames = s->channels ? (int64_t)(s->oi.samples / (uint64_t)s->channels) : 0;
     // sfb row / version from the first frame header the index or the start offset points at
     size_t first = (size_t)(s->oi.index.empty() ? s->oi.start_offset : s->oi.index[0].offset);

@@ -38,7 +38,7 @@ struct l3b_stream_desc_t
     ubyte nch;
     ubyte sr_idx;
     ubyte mpeg1;
-    ubyte reserved;
+    ubyte layer;      // 0 / 3: Layer III; 1 / 2: Layer I / II
     uint reserved2;
 }
 

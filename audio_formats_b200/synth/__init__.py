@@ -18,9 +18,9 @@ _SO = _HERE / "libl3synth.so"
 
 
 def build(force: bool = False) -> Path:
-    src = _HERE / "l3synth.c"
-    if force or not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-o", str(_SO), str(src)])
+    srcs = [_HERE / "l3synth.c", _HERE / "l12synth.c"]
+    if force or not _SO.exists() or any(_SO.stat().st_mtime < s.stat().st_mtime for s in srcs):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-o", str(_SO), *[str(s) for s in srcs]])
     return _SO
 
 
@@ -38,6 +38,12 @@ class _Info(C.Structure):
                 ("sr_idx", C.c_int), ("bytes", C.c_longlong)]
 
 
+class _L12Params(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("layer", C.c_int), ("hz", C.c_int), ("nch", C.c_int), ("bitrate_kbps", C.c_int),
+                ("nframes", C.c_int), ("joint", C.c_int), ("crc", C.c_int), ("padding", C.c_int), ("fill", C.c_int),
+                ("ref_syntax", C.c_int), ("all_alloc", C.c_int)]
+
+
 _lib = None
 
 
@@ -46,6 +52,10 @@ def _load():
     if _lib is None:
         build()
         _lib = C.CDLL(str(_SO))
+        _lib.l12s_max_bytes.restype = C.c_size_t
+        _lib.l12s_max_bytes.argtypes = [C.POINTER(_L12Params)]
+        _lib.l12s_generate.restype = C.c_longlong
+        _lib.l12s_generate.argtypes = [C.POINTER(_L12Params), C.c_void_p, C.c_size_t]
         _lib.l3s_max_bytes.restype = C.c_size_t
         _lib.l3s_max_bytes.argtypes = [C.POINTER(_Params)]
         _lib.l3s_generate.restype = C.c_longlong
@@ -161,3 +171,31 @@ def config4_params(seed: int, seconds: float = 30.0) -> SynthParams:
 def config5_params(seed: int, seconds: float = 180.0) -> SynthParams:
     """180 s, 44.1 kHz stereo 320 kbps."""
     return SynthParams.for_seconds(seconds, seed=seed, bitrate_kbps=320, reservoir=1, level=12.0, gain_base=186)
+
+
+@dataclass
+class L12Params:
+    """Synthetic MPEG-1/2 Layer I / Layer II stream (l12synth.c)."""
+    seed: int = 1
+    layer: int = 2
+    hz: int = 44100
+    nch: int = 2
+    bitrate_kbps: int = 192
+    nframes: int = 60
+    joint: int = 0
+    crc: int = 0
+    padding: int = 1
+    fill: int = 90
+    ref_syntax: int = 1   # Layer II written the way the D reference reads it (a scfsi field for every band-channel entry)
+    all_alloc: int = 0    # every band allocated: with plain stereo the reference's reading and ISO syntax coincide
+
+
+def generate_l12(params: L12Params) -> bytes:
+    lib = _load()
+    p = _L12Params(**asdict(params))
+    cap = lib.l12s_max_bytes(C.byref(p))
+    buf = np.zeros(cap, dtype=np.uint8)
+    n = lib.l12s_generate(C.byref(p), buf.ctypes.data, cap)
+    if n < 0:
+        raise ValueError(f"l12s_generate failed with {n} for {params}")
+    return buf[:n].tobytes()

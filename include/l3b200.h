@@ -35,7 +35,7 @@ extern "C" {
 #define L3B_E_USER (-4)      /* MP3D_E_USER    minimp3_ex.d:33 (also: "not an MP3") */
 #define L3B_E_DECODE (-5)    /* MP3D_E_DECODE  minimp3_ex.d:34 */
 #define L3B_E_NOGPU (-16)    /* no usable CUDA device / kernel launch failed (ours) */
-#define L3B_E_UNSUPPORTED (-17) /* Layer I/II stream: outside this path */
+#define L3B_E_UNSUPPORTED (-17) /* reserved (was: Layer I/II stream, which now decodes) */
 
 /* ------------------------------------------------------------------------------------------------
  * Descriptors: what the host prepass hands to the GPU.
@@ -56,7 +56,7 @@ typedef struct {
 typedef struct {
     uint64_t maindata_off;   /* byte offset of this stream's main-data blob inside the batch blob (16-byte aligned) */
     uint32_t maindata_bytes; /* valid bytes; the blob must be followed by >= 16 readable zero bytes */
-    uint32_t n_granules;     /* decodable granules, decode order */
+    uint32_t n_granules;     /* decodable granules, decode order (Layer III: 576 frames each; Layer I / II: 384 frames each) */
     uint64_t first_grch;     /* index of the stream's first descriptor in the batch descriptor array */
     uint64_t pcm_off;        /* float offset of the stream's first delivered sample in the PCM output */
     uint64_t pcm_skip;       /* interleaved samples to drop from the front of the decoded signal (encoder delay, minimp3_ex.d:862-867) */
@@ -64,7 +64,9 @@ typedef struct {
     uint8_t nch;             /* 1 or 2 */
     uint8_t sr_idx;          /* row of the sfb tables, minimp3.d:523 */
     uint8_t mpeg1;           /* 1: MPEG-1 (2 granules/frame), 0: MPEG-2 / 2.5 LSF */
-    uint8_t reserved;
+    uint8_t layer;           /* 0 (or 3): Layer III; 1 / 2: Layer I / II -- descriptors then carry, per 12-slot granule and channel:
+                                bit_start = first bit of the frame body in the stream's blob, w1 = header bytes 1..3,
+                                w2[0:2] = index of the granule inside its frame, w3[31] = state_reset_before */
     uint32_t reserved2;
 } l3b_stream_desc_t;
 

@@ -1023,6 +1023,159 @@ static int find_frame(const uint8_t* mp3, int mp3_bytes, int* free_format_bytes,
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Layer I / II (minimp3.d:286-484)                                                             */
+#define H_GET_STEREO_MODE(h) (((h)[3] >> 6) & 3)
+#define H_GET_STEREO_MODE_EXT(h) (((h)[3] >> 4) & 3)
+#define MODE_MONO 3
+#define MODE_JOINT_STEREO 1
+
+typedef struct {                 /* L12_scale_info, minimp3.d:177-183 */
+    float scf[3 * 64];
+    uint8_t total_bands, stereo_bands, bitalloc[64], scfcod[64];
+} l12_scale_info_t;
+
+typedef struct { uint8_t tab_offset, code_tab_width, band_count; } l12_subband_alloc_t;   /* minimp3.d:172-175 */
+
+/* minimp3.d:284-350 */
+static const l12_subband_alloc_t* l12_subband_alloc_table(const uint8_t* hdr, l12_scale_info_t* sci)
+{
+    static const l12_subband_alloc_t g_alloc_L1[] = { { 76, 4, 32 } };
+    static const l12_subband_alloc_t g_alloc_L2M2[] = { { 60, 4, 4 }, { 44, 3, 7 }, { 44, 2, 19 } };
+    static const l12_subband_alloc_t g_alloc_L2M1[] = { { 0, 4, 3 }, { 16, 4, 8 }, { 32, 3, 12 }, { 40, 2, 7 } };
+    static const l12_subband_alloc_t g_alloc_L2M1_lowrate[] = { { 44, 4, 2 }, { 44, 3, 10 } };
+    const l12_subband_alloc_t* alloc;
+    int mode = H_GET_STEREO_MODE(hdr);
+    int nbands, stereo_bands = (mode == MODE_MONO) ? 0 : (mode == MODE_JOINT_STEREO) ? (H_GET_STEREO_MODE_EXT(hdr) << 2) + 4 : 32;
+
+    if (H_IS_LAYER_1(hdr)) {
+        alloc = g_alloc_L1;
+        nbands = 32;
+    } else if (!H_TEST_MPEG1(hdr)) {
+        alloc = g_alloc_L2M2;
+        nbands = 30;
+    } else {
+        int sample_rate_idx = H_GET_SAMPLE_RATE(hdr);
+        unsigned kbps = l3o_hdr_bitrate_kbps(hdr) >> (int)(mode != MODE_MONO);
+        if (!kbps) kbps = 192; /* free-format */
+        alloc = g_alloc_L2M1;
+        nbands = 27;
+        if (kbps < 56) {
+            alloc = g_alloc_L2M1_lowrate;
+            nbands = sample_rate_idx == 2 ? 12 : 8;
+        } else if (kbps >= 96 && sample_rate_idx != 1) {
+            nbands = 30;
+        }
+    }
+    sci->total_bands = (uint8_t)nbands;
+    sci->stereo_bands = (uint8_t)imin(stereo_bands, nbands);
+    return alloc;
+}
+
+/* minimp3.d:352-385.  The D literals are doubles converted to float by the static initialiser; so are these. */
+static void l12_read_scalefactors(bitrd_t* bs, uint8_t* pba, uint8_t* scfcod, int bands, float* scf)
+{
+    static const float g_deq_L12[18 * 3] = {
+        3.17891e-07, 2.52311e-07, 2.00259e-07, 1.36239e-07, 1.08133e-07, 8.58253e-08,
+        6.35783e-08, 5.04621e-08, 4.00518e-08, 3.07637e-08, 2.44172e-08, 1.93799e-08,
+        1.51377e-08, 1.20148e-08, 9.53615e-09, 7.50925e-09, 5.96009e-09, 4.73053e-09,
+        3.7399e-09, 2.96836e-09, 2.35599e-09, 1.86629e-09, 1.48128e-09, 1.17569e-09,
+        9.32233e-10, 7.39914e-10, 5.8727e-10, 4.65889e-10, 3.69776e-10, 2.93492e-10,
+        2.32888e-10, 1.84843e-10, 1.4671e-10, 1.1643e-10, 9.24102e-11, 7.3346e-11,
+        5.82112e-11, 4.62023e-11, 3.66708e-11, 2.91047e-11, 2.31004e-11, 1.83348e-11,
+        1.45521e-11, 1.155e-11, 9.16727e-12, 3.17891e-07, 2.52311e-07, 2.00259e-07,
+        1.90735e-07, 1.51386e-07, 1.20155e-07, 1.05964e-07, 8.41035e-08, 6.6753e-08
+    };
+    int i, m;
+    for (i = 0; i < bands; i++) {
+        float s = 0;
+        int ba = *pba++;
+        int mask = ba ? 4 + ((19 >> scfcod[i]) & 3) : 0;
+        for (m = 4; m; m >>= 1) {
+            if (mask & m) {
+                int b = (int)rd_bits(bs, 6);
+                s = g_deq_L12[ba * 3 - 6 + b % 3] * (float)(1 << 21 >> b / 3);
+            }
+            *scf++ = s;
+        }
+    }
+}
+
+/* minimp3.d:387-435 */
+static void l12_read_scale_info(const uint8_t* hdr, bitrd_t* bs, l12_scale_info_t* sci)
+{
+    static const uint8_t g_bitalloc_code_tab[] = {
+        0, 17, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16,
+        0, 17, 18, 3, 19, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16,
+        0, 17, 18, 3, 19, 4, 5, 16,
+        0, 17, 18, 16,
+        0, 17, 18, 19, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15,
+        0, 17, 18, 3, 19, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14,
+        0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16
+    };
+    const l12_subband_alloc_t* subband_alloc = l12_subband_alloc_table(hdr, sci);
+    int i, k = 0, ba_bits = 0;
+    const uint8_t* ba_code_tab = g_bitalloc_code_tab;
+
+    for (i = 0; i < sci->total_bands; i++) {
+        uint8_t ba;
+        if (i == k) {
+            k += subband_alloc->band_count;
+            ba_bits = subband_alloc->code_tab_width;
+            ba_code_tab = g_bitalloc_code_tab + subband_alloc->tab_offset;
+            subband_alloc++;
+        }
+        ba = ba_code_tab[rd_bits(bs, ba_bits)];
+        sci->bitalloc[2 * i] = ba;
+        if (i < sci->stereo_bands) ba = ba_code_tab[rd_bits(bs, ba_bits)];
+        sci->bitalloc[2 * i + 1] = sci->stereo_bands ? ba : 0;
+    }
+    for (i = 0; i < 2 * sci->total_bands; i++) {
+        uint8_t temp = H_IS_LAYER_1(hdr) ? 2 : (uint8_t)rd_bits(bs, 2);
+        sci->scfcod[i] = sci->bitalloc[i] ? temp : 6;
+    }
+    l12_read_scalefactors(bs, sci->bitalloc, sci->scfcod, sci->total_bands * 2, sci->scf);
+    for (i = sci->stereo_bands; i < sci->total_bands; i++) sci->bitalloc[2 * i + 1] = 0;
+}
+
+/* minimp3.d:437-470 */
+static int l12_dequantize_granule(float* grbuf, bitrd_t* bs, l12_scale_info_t* sci, int group_size)
+{
+    int i, j, k, choff = 576;
+    for (j = 0; j < 4; j++) {
+        float* dst = grbuf + group_size * j;
+        for (i = 0; i < 2 * sci->total_bands; i++) {
+            int ba = sci->bitalloc[i];
+            if (ba != 0) {
+                if (ba < 17) {
+                    int half = (1 << (ba - 1)) - 1;
+                    for (k = 0; k < group_size; k++) dst[k] = (float)((int)rd_bits(bs, ba) - half);
+                } else {
+                    unsigned mod = (2 << (ba - 17)) + 1;                       /* 3, 5, 9 */
+                    unsigned code = rd_bits(bs, mod + 2 - (mod >> 3));         /* 5, 7, 10 */
+                    for (k = 0; k < group_size; k++, code /= mod) dst[k] = (float)((int)(code % mod - mod / 2));
+                }
+            }
+            dst += choff;
+            choff = 18 - choff;
+        }
+    }
+    return group_size * 4;
+}
+
+/* minimp3.d:472-484 */
+static void l12_apply_scf_384(l12_scale_info_t* sci, const float* scf, float* dst)
+{
+    int i, k;
+    memcpy(dst + 576 + sci->stereo_bands * 18, dst + sci->stereo_bands * 18, (sci->total_bands - sci->stereo_bands) * 18 * sizeof(float));
+    for (i = 0; i < sci->total_bands; i++, dst += 18, scf += 6) {
+        for (k = 0; k < 12; k++) {
+            dst[k + 0] *= scf[0];
+            dst[k + 576] *= scf[3];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* frame entry (minimp3.d:1487-1581), Layer III branch only                                    */
 void l3o_init(l3o_dec_t* dec) { dec->header[0] = 0; }
 
@@ -1094,10 +1247,23 @@ int l3o_decode_frame(l3o_dec_t* dec, const uint8_t* mp3, int mp3_bytes, float* p
         save_reservoir(dec, &scratch);
         if (g_timers_on) t_timer[0] += now_s() - t0;
     } else {
-        /* Layer I/II: out of scope for this path.  The oracle reports the frame as
-         * undecodable so callers notice instead of silently producing silence. */
-        l3o_init(dec);
-        return 0;
+        /* Layer I / II (minimp3.d:1557-1579) */
+        l12_scale_info_t sci[1];
+        l12_read_scale_info(hdr, bs_frame, sci);
+        memset(scratch.grbuf[0], 0, 576 * 2 * sizeof(float));
+        for (i = 0, igr = 0; igr < 3; igr++) {
+            if (12 == (i += l12_dequantize_granule(scratch.grbuf[0] + i, bs_frame, sci, info->layer | 1))) {
+                i = 0;
+                l12_apply_scf_384(sci, sci->scf + igr, scratch.grbuf[0]);
+                synth_granule(dec->qmf_state, scratch.grbuf[0], 12, info->channels, pcm, scratch.syn[0], NULL);
+                memset(scratch.grbuf[0], 0, 576 * 2 * sizeof(float));
+                pcm += 384 * info->channels;
+            }
+            if (bs_frame->pos > bs_frame->limit) {
+                l3o_init(dec);
+                return 0;
+            }
+        }
     }
     return success * l3o_hdr_frame_samples(dec->header);
 }

@@ -154,3 +154,25 @@ def test_pow43_and_synthesis_window():
             for c in range(2):
                 assert ours[(k * 2 + c) * 15 + i] == win[p], (i, k, c)
                 p += 1
+
+
+def test_layer12_tables():
+    """audio_formats_b200/csrc/l12_tables.h against the literals of minimp3.d:284-398 (the oracle carries its own copy)."""
+    l12 = (GEN.parent / "l12_tables.h").read_text()
+
+    def mine(name, conv):
+        m = re.search(re.escape(name) + r"\[[^=]*=\s*\{(.*?)\};", l12, re.S)
+        assert m, name
+        return [conv(x) for x in re.findall(NUM, m.group(1))]
+
+    assert mine("L12_BITALLOC_CODE_TAB", int) == ref_array("g_bitalloc_code_tab", int)
+    ref_deq = np.array(ref_array("g_deq_L12", float), np.float64).astype(np.float32)      # D: double literals converted to float
+    my_deq = np.array(mine("L12_DEQ", float), np.float64).astype(np.float32)
+    assert len(ref_deq) == 54 and np.array_equal(ref_deq.view(np.uint32), my_deq.view(np.uint32))
+    src = REF.read_text()
+    for ref_name, my_name in (("g_alloc_L1", "L12_ALLOC_L1"), ("g_alloc_L2M2", "L12_ALLOC_L2M2"), ("g_alloc_L2M1", "L12_ALLOC_L2M1"),
+                              ("g_alloc_L2M1_lowrate", "L12_ALLOC_L2M1_LOWRATE")):
+        m = re.search(re.escape(ref_name) + r"\s*=\s*\[(.*?)\];", src, re.S)
+        assert m, ref_name
+        want = [int(x) for x in re.findall(r"L12_subband_alloc_t\(([^)]*)\)", m.group(1)) for x in x.split(",")]
+        assert mine(my_name, int)[-len(want):] == want and len(want) % 3 == 0, ref_name

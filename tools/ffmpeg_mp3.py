@@ -76,16 +76,16 @@ def _load():
     return _libs
 
 
-def decode_frames(data: bytes, frame_offsets, frame_sizes) -> np.ndarray:
-    """Decode the given frames (byte offset + size each, in stream order) with FFmpeg's mp3float.
+def decode_frames(data: bytes, frame_offsets, frame_sizes, decoder: bytes = b"mp3float") -> np.ndarray:
+    """Decode the given frames (byte offset + size each, in stream order) with FFmpeg's mp3float (or mp2float / mp1float).
     Returns float32 [total_samples_per_channel, channels]."""
     libs = _load()
     if libs is None:
         raise RuntimeError("libavcodec 62 not found")
     U, A = libs
-    codec = A.avcodec_find_decoder_by_name(b"mp3float")
+    codec = A.avcodec_find_decoder_by_name(decoder)
     if not codec:
-        raise RuntimeError("mp3float decoder missing from libavcodec")
+        raise RuntimeError(f"{decoder.decode()} decoder missing from libavcodec")
     ctx = C.c_void_p(A.avcodec_alloc_context3(codec))
     if A.avcodec_open2(ctx, codec, None) < 0:
         raise RuntimeError("avcodec_open2 failed")
