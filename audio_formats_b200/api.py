@@ -126,6 +126,15 @@ def load_library():
         "l3b_scan_fill_stream_desc": (None, [vp, C.POINTER(StreamDesc)]),
         "l3b_scans_assemble": (C.c_int, [C.POINTER(vp), C.c_uint32, vp, C.c_uint64, vp, C.c_uint64, vp, C.POINTER(Batch)]),
         "l3b_decode_scans": (C.c_int, [vp, C.POINTER(vp), C.c_uint32, C.POINTER(vp), C.POINTER(C.c_int32)]),
+        "l3b_raw_open": (C.c_int, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+        "l3b_raw_device_streams": (C.c_uint32, [vp]),
+        "l3b_raw_prepass_ms": (C.c_float, [vp]),
+        "l3b_raw_channels": (C.c_int, [vp, C.c_uint32]),
+        "l3b_raw_samplerate": (C.c_int, [vp, C.c_uint32]),
+        "l3b_raw_samples": (C.c_uint64, [vp, C.c_uint32]),
+        "l3b_raw_status": (C.c_int, [vp, C.c_uint32]),
+        "l3b_raw_decode": (C.c_int, [vp, C.POINTER(vp)]),
+        "l3b_raw_free": (None, [vp]),
         "l3b_pipeline_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(PipelineOpts), C.POINTER(vp)]),
         "l3b_pipeline_destroy": (None, [vp]),
         "l3b_pipeline_decode": (C.c_int, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_uint32, vp, C.c_uint64,
@@ -244,6 +253,41 @@ class Context:
 
     def decode(self, datas: Sequence[bytes]) -> list[np.ndarray]:
         return self.decode_scans([Scan(d) for d in datas])
+
+    def decode_raw(self, datas: Sequence[bytes], flags: int = 0):
+        """Batch decode with the prepass on the GPU (l3b_raw_*): returns (list of [frames, channels] arrays or None,
+        info dict with the number of streams whose prepass ran on the device and its kernel time)."""
+        n = len(datas)
+        ptrs = (C.c_char_p * n)(*datas)
+        sizes = (C.c_size_t * n)(*[len(d) for d in datas])
+        h = C.c_void_p()
+        self._check(self._L.l3b_raw_open(self._h, ptrs, sizes, n, flags, C.byref(h)))
+        try:
+            dt = np.int16 if flags & OUT_S16 else np.float32
+            status = [self._L.l3b_raw_status(h, i) for i in range(n)]
+            outs = [np.empty(self._L.l3b_raw_samples(h, i), dtype=dt) for i in range(n)]
+            ps = (C.c_void_p * n)(*[o.ctypes.data if o.size else None for o in outs])
+            self._check(self._L.l3b_raw_decode(h, ps))
+            res = [o.reshape(-1, self._L.l3b_raw_channels(h, i)) if self._L.l3b_raw_channels(h, i) else None for i, o in enumerate(outs)]
+            info = {"device_streams": self._L.l3b_raw_device_streams(h), "prepass_ms": self._L.l3b_raw_prepass_ms(h), "status": status}
+        finally:
+            self._L.l3b_raw_free(h)
+        return res, info
+
+    def raw_prepass(self, datas: Sequence[bytes]) -> dict:
+        """Only the prepass of decode_raw (upload of the raw files + the device kernels + layout of the batch), for timing."""
+        import time
+        n = len(datas)
+        ptrs = (C.c_char_p * n)(*datas)
+        sizes = (C.c_size_t * n)(*[len(d) for d in datas])
+        h = C.c_void_p()
+        t0 = time.perf_counter()
+        self._check(self._L.l3b_raw_open(self._h, ptrs, sizes, n, 0, C.byref(h)))
+        wall = time.perf_counter() - t0
+        info = {"device_streams": self._L.l3b_raw_device_streams(h), "streams": n, "prepass_kernels_ms": self._L.l3b_raw_prepass_ms(h),
+                "open_wall_ms": wall * 1e3}
+        self._L.l3b_raw_free(h)
+        return info
 
     # ---- resident batches (throughput work) ----------------------------------------------------
     def upload(self, batch: "HostBatch") -> "ResidentBatch":

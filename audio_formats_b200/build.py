@@ -8,7 +8,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libl3b200.so"
-SOURCES = ["l3_kernels.cu", "l3_entropy.cu", "l12_kernels.cu", "l3_ctx.cu", "l3_host.cpp", "l3_stream.cpp", "l3_pipeline.cpp"]
+SOURCES = ["l3_kernels.cu", "l3_entropy.cu", "l12_kernels.cu", "l3_ctx.cu", "l3_raw.cu", "l3_host.cpp", "l3_stream.cpp", "l3_pipeline.cpp"]
 HEADERS = ["l3_kernels.cuh", "l3_desc.cuh", "l3_host.hpp", "l3_format.hpp", "l3_device_tables.hpp", "l3_tables_gen.h", "l12_tables.h",
            "../../include/l3b200.h"]
 

@@ -258,10 +258,11 @@ void l3b_batch_free(l3b_ctx_t* c, l3b_resident_t* r) {
     delete r;
 }
 
-static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inout, bool reuse) {
+// device_inputs: the blob and the descriptors are produced on the device (l3_raw.cu), only the stream table comes from the host
+static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inout, bool reuse, bool device_inputs = false) {
     if (!c || !b || !inout) return L3B_E_PARAM;
     if (!reuse) *inout = nullptr;
-    if (!b->n_streams || !b->streams || (b->n_grch && !b->grch) || (b->maindata_bytes && !b->maindata)) {
+    if (!b->n_streams || !b->streams || (!device_inputs && ((b->n_grch && !b->grch) || (b->maindata_bytes && !b->maindata)))) {
         c->err = "empty or inconsistent batch";
         return L3B_E_PARAM;
     }
@@ -395,8 +396,8 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     r->pcm_floats = b->pcm_floats;
     r->subs = subs;
     CU_TRY_R(cudaMemsetAsync(r->d_blob + b->maindata_bytes, 0, 64, c->stream));
-    if (b->maindata_bytes) CU_TRY_R(cudaMemcpyAsync(r->d_blob, b->maindata, b->maindata_bytes, cudaMemcpyHostToDevice, c->stream));
-    if (b->n_grch) CU_TRY_R(cudaMemcpyAsync(r->d_grch, b->grch, b->n_grch * sizeof(l3b_grch_desc_t), cudaMemcpyHostToDevice, c->stream));
+    if (b->maindata_bytes && !device_inputs) CU_TRY_R(cudaMemcpyAsync(r->d_blob, b->maindata, b->maindata_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (b->n_grch && !device_inputs) CU_TRY_R(cudaMemcpyAsync(r->d_grch, b->grch, b->n_grch * sizeof(l3b_grch_desc_t), cudaMemcpyHostToDevice, c->stream));
     CU_TRY_R(cudaMemcpyAsync(r->d_streams, b->streams, b->n_streams * sizeof(l3b_stream_desc_t), cudaMemcpyHostToDevice, c->stream));
     for (int k = 0; k < 4; k++)
         if (r->n_tiles[k])
@@ -690,3 +691,15 @@ int l3b_decode_scans(l3b_ctx_t* c, l3b_scan_t* const* scans, uint32_t n, float* 
 }
 
 }  // extern "C"
+
+// internal entry points for l3_raw.cu (the device prepass fills the blob and the descriptor table itself)
+namespace l3b {
+int resident_for_device_inputs(l3b_ctx_t* c, const l3b_batch_t* shape, l3b_resident_t** inout) { return upload_impl(c, shape, inout, false, true); }
+uint8_t* resident_blob(l3b_resident_t* r) { return r->d_blob; }
+l3b_grch_desc_t* resident_descs(l3b_resident_t* r) { return r->d_grch; }
+const uint8_t* ctx_sfb_width(l3b_ctx_t* c) { return c->t.sfb_width; }
+cudaStream_t ctx_stream(l3b_ctx_t* c) { return c->stream; }
+std::string& ctx_err(l3b_ctx_t* c) { return c->err; }
+int ctx_device(l3b_ctx_t* c) { return c->device; }
+}  // namespace l3b
+

@@ -10,6 +10,12 @@
 #include "l12_tables.h"
 #include "l3_tables_gen.h"
 
+#ifdef __CUDACC__
+#define L3B_HD __host__ __device__
+#else
+#define L3B_HD
+#endif
+
 namespace l3b {
 
 constexpr int kHdrSize = 4;
@@ -20,51 +26,53 @@ constexpr int kMaxReservoir = 511;         // minimp3.d:58
 // ---- header field access (minimp3.d:65-148) -----------------------------------------------------
 struct Hdr {
     const uint8_t* h;
-    explicit Hdr(const uint8_t* p) : h(p) {}
-    bool mono() const { return (h[3] & 0xC0) == 0xC0; }
-    bool free_format() const { return (h[2] & 0xF0) == 0; }
-    bool has_crc() const { return !(h[1] & 1); }
-    bool mpeg1() const { return (h[1] & 0x08) != 0; }
-    bool not_mpeg25() const { return (h[1] & 0x10) != 0; }
-    int layer_bits() const { return (h[1] >> 1) & 3; }
-    int bitrate_idx() const { return h[2] >> 4; }
-    int sr_bits() const { return (h[2] >> 2) & 3; }
-    bool layer1() const { return (h[1] & 6) == 6; }
-    bool frame576() const { return (h[1] & 14) == 2; }
+    L3B_HD explicit Hdr(const uint8_t* p) : h(p) {}
+    L3B_HD bool mono() const { return (h[3] & 0xC0) == 0xC0; }
+    L3B_HD bool free_format() const { return (h[2] & 0xF0) == 0; }
+    L3B_HD bool has_crc() const { return !(h[1] & 1); }
+    L3B_HD bool mpeg1() const { return (h[1] & 0x08) != 0; }
+    L3B_HD bool not_mpeg25() const { return (h[1] & 0x10) != 0; }
+    L3B_HD int layer_bits() const { return (h[1] >> 1) & 3; }
+    L3B_HD int bitrate_idx() const { return h[2] >> 4; }
+    L3B_HD int sr_bits() const { return (h[2] >> 2) & 3; }
+    L3B_HD bool layer1() const { return (h[1] & 6) == 6; }
+    L3B_HD bool frame576() const { return (h[1] & 14) == 2; }
     // 0..2 MPEG-2.5, 3..5 MPEG-2, 6..8 MPEG-1 (minimp3.d:135-138)
-    int my_sample_rate() const { return sr_bits() + (((h[1] >> 3) & 1) + ((h[1] >> 4) & 1)) * 3; }
-    int sfb_row() const { int v = my_sample_rate(); return v - (v != 0); }  // minimp3.d:523
-    int channels() const { return mono() ? 1 : 2; }
-    int layer() const { return 4 - layer_bits(); }
+    L3B_HD int my_sample_rate() const { return sr_bits() + (((h[1] >> 3) & 1) + ((h[1] >> 4) & 1)) * 3; }
+    L3B_HD int sfb_row() const { int v = my_sample_rate(); return v - (v != 0); }  // minimp3.d:523
+    L3B_HD int channels() const { return mono() ? 1 : 2; }
+    L3B_HD int layer() const { return 4 - layer_bits(); }
 
     // minimp3.d:232-239
-    bool valid() const {
+    L3B_HD bool valid() const {
         return h[0] == 0xff && ((h[1] & 0xF0) == 0xf0 || (h[1] & 0xFE) == 0xe2) && layer_bits() != 0 &&
                bitrate_idx() != 15 && sr_bits() != 3;
     }
     // minimp3.d:249-257
-    unsigned bitrate_kbps() const {
-        return 2u * L3_HALFRATE[((mpeg1() ? 1 : 0) * 3 + (layer_bits() - 1)) * 15 + bitrate_idx()];
+    L3B_HD unsigned bitrate_kbps_t(const uint8_t* halfrate) const {   // halfrate: L3_HALFRATE, or its copy in device memory
+        return 2u * halfrate[((mpeg1() ? 1 : 0) * 3 + (layer_bits() - 1)) * 15 + bitrate_idx()];
     }
+    unsigned bitrate_kbps() const { return bitrate_kbps_t(L3_HALFRATE); }
     // minimp3.d:259-263
-    unsigned sample_rate_hz() const {
-        static const unsigned hz[3] = {44100, 48000, 32000};
-        return hz[sr_bits()] >> (mpeg1() ? 0 : 1) >> (not_mpeg25() ? 0 : 1);
+    L3B_HD unsigned sample_rate_hz() const {
+        const unsigned hz = sr_bits() == 0 ? 44100u : (sr_bits() == 1 ? 48000u : 32000u);
+        return hz >> (mpeg1() ? 0 : 1) >> (not_mpeg25() ? 0 : 1);
     }
     // minimp3.d:265-268
-    unsigned frame_samples() const { return layer1() ? 384u : (1152u >> (frame576() ? 1 : 0)); }
+    L3B_HD unsigned frame_samples() const { return layer1() ? 384u : (1152u >> (frame576() ? 1 : 0)); }
     // minimp3.d:270-278
-    int frame_bytes(int free_format_size) const {
-        int fb = (int)(frame_samples() * bitrate_kbps() * 125 / sample_rate_hz());
+    L3B_HD int frame_bytes_t(const uint8_t* halfrate, int free_format_size) const {
+        int fb = (int)(frame_samples() * bitrate_kbps_t(halfrate) * 125 / sample_rate_hz());
         if (layer1()) fb &= ~3;
         return fb ? fb : free_format_size;
     }
+    int frame_bytes(int free_format_size) const { return frame_bytes_t(L3_HALFRATE, free_format_size); }
     // minimp3.d:280-283
-    int padding() const { return (h[2] & 2) ? (layer1() ? 4 : 1) : 0; }
+    L3B_HD int padding() const { return (h[2] & 2) ? (layer1() ? 4 : 1) : 0; }
 };
 
 // minimp3.d:241-247: same stream family (version/layer/sample rate/free-format-ness)
-inline bool hdr_compatible(const uint8_t* a, const uint8_t* b) {
+L3B_HD inline bool hdr_compatible(const uint8_t* a, const uint8_t* b) {
     return Hdr(b).valid() && ((a[1] ^ b[1]) & 0xFE) == 0 && ((a[2] ^ b[2]) & 0x0C) == 0 &&
            !(Hdr(a).free_format() ^ Hdr(b).free_format());
 }
@@ -109,8 +117,8 @@ inline int find_frame(const uint8_t* p, int bytes, int* free_format_bytes, int* 
 struct BitReader {
     const uint8_t* buf;
     int pos, limit;
-    BitReader(const uint8_t* d, int bytes) : buf(d), pos(0), limit(bytes * 8) {}
-    uint32_t get(int n) {
+    L3B_HD BitReader(const uint8_t* d, int bytes) : buf(d), pos(0), limit(bytes * 8) {}
+    L3B_HD uint32_t get(int n) {
         int p = pos;
         pos += n;
         if (pos > limit) return 0;  // still advances
@@ -207,8 +215,20 @@ struct GranuleInfo {
     const uint8_t* sfbtab;
 };
 
+// scalefactor-band width rows: kind 0 long, 1 short, 2 mixed (the host's literal tables; the device prepass passes a functor
+// over their copy in device memory, DeviceTables::sfb_width)
+struct HostSfbRows {
+    const uint8_t* operator()(int row, int kind) const {
+        return kind == 0 ? L3_SFB_LONG + row * 23 : (kind == 1 ? L3_SFB_SHORT + row * 40 : L3_SFB_MIXED + row * 40);
+    }
+};
+
 // Returns main_data_begin, or -1 when the frame must be dropped (minimp3.d:545, 557, 605).
-inline int parse_side_info(BitReader& bs, GranuleInfo* gr, const uint8_t* hdr_bytes) {
+#ifdef __CUDACC__
+#pragma nv_exec_check_disable   // instantiated with a host-only functor on the host and a device-side one on the device
+#endif
+template <class Rows>
+L3B_HD inline int parse_side_info_t(BitReader& bs, GranuleInfo* gr, const uint8_t* hdr_bytes, const Rows& rows) {
     Hdr hdr(hdr_bytes);
     const int row = hdr.sfb_row();
     int n = hdr.mono() ? 1 : 2;
@@ -229,7 +249,7 @@ inline int parse_side_info(BitReader& bs, GranuleInfo* gr, const uint8_t* hdr_by
         if (gr->big_values > 288) return -1;
         gr->global_gain = (uint8_t)bs.get(8);
         gr->scalefac_compress = (uint16_t)bs.get(hdr.mpeg1() ? 4 : 9);
-        gr->sfbtab = L3_SFB_LONG + row * 23;
+        gr->sfbtab = rows(row, 0);
         gr->n_long_sfb = 22;
         gr->n_short_sfb = 0;
         unsigned tables;
@@ -243,11 +263,11 @@ inline int parse_side_info(BitReader& bs, GranuleInfo* gr, const uint8_t* hdr_by
                 scfsi &= 0x0F0F;
                 if (!gr->mixed_block_flag) {
                     gr->region_count[0] = 8;
-                    gr->sfbtab = L3_SFB_SHORT + row * 40;
+                    gr->sfbtab = rows(row, 1);
                     gr->n_long_sfb = 0;
                     gr->n_short_sfb = 39;
                 } else {
-                    gr->sfbtab = L3_SFB_MIXED + row * 40;
+                    gr->sfbtab = rows(row, 2);
                     gr->n_long_sfb = hdr.mpeg1() ? 8 : 6;
                     gr->n_short_sfb = 30;
                 }
@@ -278,11 +298,12 @@ inline int parse_side_info(BitReader& bs, GranuleInfo* gr, const uint8_t* hdr_by
     if (part_23_sum + bs.pos > bs.limit + main_data_begin * 8) return -1;
     return main_data_begin;
 }
+inline int parse_side_info(BitReader& bs, GranuleInfo* gr, const uint8_t* hdr_bytes) { return parse_side_info_t(bs, gr, hdr_bytes, HostSfbRows()); }
 
 // Pack one granule-channel into the 16-byte device descriptor (layout in l3b200.h).
 // The region boundaries are converted from sfb counts to coefficient indices here, so the entropy
 // kernel never needs the sfb tables (region loop of minimp3.d:780-853).
-inline l3b_grch_desc_t pack_desc(const GranuleInfo& g, uint32_t bit_start, uint8_t hdr3, bool second_granule,
+L3B_HD inline l3b_grch_desc_t pack_desc(const GranuleInfo& g, uint32_t bit_start, uint8_t hdr3, bool second_granule,
                                  bool reset_before) {
     int acc = 0, i = 0;
     for (; i <= g.region_count[0] && g.sfbtab[i]; i++) acc += g.sfbtab[i];

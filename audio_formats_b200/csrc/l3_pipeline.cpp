@@ -238,7 +238,7 @@ void lane_worker(Run* R, int d, int k) {
                 r.status = l3b_scan_error(good[j]);   // a sticky decode error met mid-stream (what was decoded before it is delivered)
                 r.pcm_off = base + sd[j].pcm_off;
                 r.frames = nch ? sd[j].pcm_count / (uint64_t)nch : 0;
-                r.device = D.id;
+                r.device = d;
             }
         }
         for (uint32_t si : W.streams) { l3b_scan_free(R->scans[si]); R->scans[si] = nullptr; }

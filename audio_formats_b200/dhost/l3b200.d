@@ -151,6 +151,18 @@ int l3b_pipeline_decode(l3b_pipeline_t* p, const(ubyte*)* data, const(size_t)* s
 int l3b_pipeline_profile(l3b_pipeline_t* p, double* seconds6);
 const(char)* l3b_pipeline_last_error(const(l3b_pipeline_t)* p);
 
+struct l3b_raw;
+alias l3b_raw_t = l3b_raw;
+int l3b_raw_open(l3b_ctx_t* ctx, const(ubyte*)* data, const(size_t)* size, uint n, uint flags, l3b_raw_t** outRaw);
+uint l3b_raw_device_streams(const(l3b_raw_t)* r);
+float l3b_raw_prepass_ms(const(l3b_raw_t)* r);
+int l3b_raw_channels(const(l3b_raw_t)* r, uint i);
+int l3b_raw_samplerate(const(l3b_raw_t)* r, uint i);
+ulong l3b_raw_samples(const(l3b_raw_t)* r, uint i);
+int l3b_raw_status(const(l3b_raw_t)* r, uint i);
+int l3b_raw_decode(l3b_raw_t* r, void** pcm);
+void l3b_raw_free(l3b_raw_t* r);
+
 int l3b_stream_open_callbacks(l3b_ctx_t* ctx, l3b_read_cb read, l3b_seek_cb seek, void* user, l3b_stream_t** outStream);
 int l3b_stream_open_memory(l3b_ctx_t* ctx, const(ubyte)* data, size_t size, l3b_stream_t** outStream);
 int l3b_stream_open_file(l3b_ctx_t* ctx, const(char)* path, l3b_stream_t** outStream);

@@ -543,6 +543,18 @@ def main():
                        "seconds_per_step_by_phase_summed_over_threads": prof32}}
     pin_pcm.free()
 
+    # ---- the prepass on the GPU (l3b_raw_open: frame walk, side info, reservoir, main-data gather as kernels) vs on the host ----
+    device_prepass = None
+    if rank == 0 and rb is None:
+        try:
+            ctx.raw_prepass(datas[:8])
+            device_prepass = ctx.raw_prepass(datas)
+            device_prepass["host_prepass_thread_ms"] = t_scan * 1e3 * threads
+            device_prepass["note"] = ("open_wall_ms includes the H2D of the raw files from pageable memory and the allocation of the resident batch; "
+                                      "prepass_kernels_ms is the device time of the walk / side-info / reservoir kernels")
+        except api.L3BError as exc:
+            device_prepass = {"error": str(exc)[:200]}
+
     # ---- BASELINE config 1: the transcode example's loop (open, 1,024-frame reads) on ONE 10 s stream through AudioStream ----
     config1 = None
     if rank == 0:
@@ -594,7 +606,7 @@ def main():
                 "data": "synthetic", "config": workload_config(args),
                 "audio_seconds_per_step": total_audio, "granule_channels_per_gpu": n_grch,
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
-                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "parity": parity, "config1_transcode": config1,
+                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "parity": parity, "config1_transcode": config1, "device_prepass": device_prepass,
                 "setup": {"generate_s": t_gen, "prepass_s": t_scan, "host_threads": threads,
                           "join": "gloo (timing scalars only; no NCCL, no collective on the data path)" if world > 1 else "single process"}}
         print(json.dumps(line), flush=True)

@@ -200,7 +200,7 @@ typedef struct {
     uint64_t frames;       /* frames delivered (samples per channel) */
     int32_t channels, samplerate;
     int32_t status;        /* 0, or the negative code that made the stream undecodable / stopped it early */
-    int32_t device;        /* GPU that decoded it */
+    int32_t device;        /* position in device_ids[] of the GPU that decoded it */
 } l3b_stream_result_t;
 #define L3B_PIPELINE_PHASES 6
 int l3b_pipeline_create(const int* device_ids, int n_devices, const l3b_pipeline_opts_t* opts, l3b_pipeline_t** out);
@@ -213,6 +213,22 @@ int l3b_pipeline_decode(l3b_pipeline_t* p, const uint8_t* const* data, const siz
  * [2] upload, [3] launch, [4] PCM download incl. waiting for the kernels, [5] waiting for the prepass. */
 int l3b_pipeline_profile(l3b_pipeline_t* p, double seconds[L3B_PIPELINE_PHASES]);
 const char* l3b_pipeline_last_error(const l3b_pipeline_t* p);
+
+/* Batch entry point over RAW Layer III files with the prepass ON THE GPU (l3_raw.cu): frame walk, side-info parse, reservoir
+ * recurrence and main-data gathering run as kernels for well-formed streams (a clean chain of compatible Layer III frames
+ * between the tags, no Xing / Info tag, legal side info, not free-format); every other stream takes the host prepass
+ * (l3b_scan_memory) inside the same call, so the PCM is the host route's in all cases.  Two steps because the output sizes
+ * are only known after the prepass.  flags: L3B_OUT_S16 | L3B_MATH_FUSED. */
+typedef struct l3b_raw l3b_raw_t;
+int l3b_raw_open(l3b_ctx_t* ctx, const uint8_t* const* data, const size_t* size, uint32_t n, uint32_t flags, l3b_raw_t** out);
+uint32_t l3b_raw_device_streams(const l3b_raw_t* r);            /* streams whose prepass ran on the GPU */
+float l3b_raw_prepass_ms(const l3b_raw_t* r);                   /* device time of the three prepass kernels */
+int l3b_raw_channels(const l3b_raw_t* r, uint32_t i);
+int l3b_raw_samplerate(const l3b_raw_t* r, uint32_t i);
+uint64_t l3b_raw_samples(const l3b_raw_t* r, uint32_t i);       /* interleaved samples stream i delivers */
+int l3b_raw_status(const l3b_raw_t* r, uint32_t i);             /* 0, or the code that makes stream i undecodable */
+int l3b_raw_decode(l3b_raw_t* r, void* const* pcm);             /* pcm[i]: room for l3b_raw_samples(r, i) elements (may be NULL) */
+void l3b_raw_free(l3b_raw_t* r);
 
 /* AudioStream mirror (names follow stream.d). */
 typedef struct l3b_stream l3b_stream_t;

@@ -272,6 +272,37 @@ def test_wave_pipeline_matches_oracle(ctx):
     pin.free()
 
 
+def test_pipeline_over_several_devices_and_bad_inputs(ctx):
+    """The library's multi-GPU batch entry point (l3b_pipeline_create with a device list): streams are assigned by file,
+    longest first; here the "devices" are GPU 0 twice, which runs the same code path on one GPU.  Inputs that are not
+    MPEG audio get their status and no PCM without disturbing the others; 16-bit delivery."""
+    import audio_formats_b200 as af
+    import oracle
+    from audio_formats_b200 import api, synth
+    streams = [synth.generate(synth.config4_params(s, 1.0 + 0.25 * (s % 5))) for s in range(200, 230)]
+    datas = [s.data for s in streams]
+    datas[7] = b"this is not an MPEG audio stream" * 40
+    datas[19] = datas[19][:9]
+    refs = [oracle.decode_all(d)[0] if i not in (7, 19) else None for i, d in enumerate(datas)]
+    total = sum(r.size for r in refs if r is not None)
+    pin = api.PinnedBuffer(2 * (total + 16 * len(datas) + 64))
+    out = pin.view(np.int16)
+    pipe = af.BatchPipeline(device=[0, 0], lanes=2, wave_streams=4, prepass_threads=3, s16=True)
+    info = pipe.decode_into(datas, out)
+    assert info[7] is None and info[19] is None and pipe.status[7] == api.E_USER and pipe.status[19] != 0
+    loads = [0, 0]
+    for i, (inf, ref) in enumerate(zip(info, refs)):
+        if ref is None:
+            continue
+        off, frames, ch, hz = inf
+        assert (frames, ch) == ref.shape
+        assert np.array_equal(out[off:off + frames * ch].reshape(frames, ch).astype(np.int32), q16(ref)), i
+        loads[pipe.device_of[i]] += len(datas[i])
+    assert min(loads) > 0.8 * max(loads)          # longest-first assignment balances the two halves by bytes
+    pipe.close()
+    pin.free()
+
+
 def test_large_batch_sampled_against_oracle_and_checksums(ctx):
     """A config-2 shaped batch too big to check stream by stream on the CPU in seconds: 192 x 60 s streams
     (1.76 M granule-channels).  A seeded sample is compared bit-exactly with the oracle; every stream is checked

@@ -164,12 +164,8 @@ def _frame_offsets(data: bytes):
     return offs
 
 
-@pytest.mark.parametrize("seed", range(24))
-def test_header_level_fuzz(built, seed):
-    """Damage aimed at the frame headers of streams long enough for the 128 KiB window to slide: flipped header bits
-    (version, layer, bitrate, sample rate, padding, mode), a few garbage bytes between frames, a duplicated frame, frames
-    of another format spliced in.  The index pass verifies its ten-header sync chain incrementally; whatever it decides
-    has to be what the reference's frame-by-frame search decides (same length, same delivered samples, same granules)."""
+def header_fuzz_stream(seed):
+    """The damaged stream of test_header_level_fuzz (also decoded by tests/test_raw_gpu.py); returns (bytes, kind)."""
     from audio_formats_b200 import synth
     rng = np.random.default_rng(4000 + seed)
     p = synth.SynthParams(seed=300 + seed, nframes=int(rng.integers(330, 420)), bitrate_kbps=int(rng.choice([128, 192, 320])),
@@ -199,7 +195,17 @@ def test_header_level_fuzz(built, seed):
             b[offs[k]] = 0x00
     else:              # cut the stream inside the last 16 KiB in several ways (end-of-buffer rule of the chain)
         b = b[: offs[len(offs) - int(rng.integers(1, 12))] + int(rng.integers(0, 300))]
-    sc, pcm, taps = scan_vs_oracle(bytes(b), f"header fuzz {kind}/{seed}")
+    return bytes(b), kind
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_header_level_fuzz(built, seed):
+    """Damage aimed at the frame headers of streams long enough for the 128 KiB window to slide: flipped header bits
+    (version, layer, bitrate, sample rate, padding, mode), a few garbage bytes between frames, a duplicated frame, frames
+    of another format spliced in.  The index pass verifies its ten-header sync chain incrementally; whatever it decides
+    has to be what the reference's frame-by-frame search decides (same length, same delivered samples, same granules)."""
+    data, kind = header_fuzz_stream(seed)
+    sc, pcm, taps = scan_vs_oracle(data, f"header fuzz {kind}/{seed}")
     assert sc.granules == len(taps)
 
 
