@@ -56,7 +56,21 @@ void upload_constants() {
 //   FUSED = true   tolerance mode: multiply-adds of the reference are contracted into FFMA2 by hand (one rounding
 //                  instead of two).  Not bit-identical; measured against the north star's 1e-5 FS / 99.99 % bar.
 
-#define L3B_PHASE_SYNC() __syncthreads()
+// The warps of a CTA run the stages in lockstep (every warp owns its buffers; the barriers are there for instruction-cache
+// locality only).  L3B_EXP_SYNCS: A/B builds -- 0 none, 1 only the first, 2 only the second.
+#if defined(L3B_EXP_SYNCS) && L3B_EXP_SYNCS == 0
+#define L3B_PHASE_SYNC1() __syncwarp()
+#define L3B_PHASE_SYNC2() __syncwarp()
+#elif defined(L3B_EXP_SYNCS) && L3B_EXP_SYNCS == 1
+#define L3B_PHASE_SYNC1() __syncthreads()
+#define L3B_PHASE_SYNC2() __syncwarp()
+#elif defined(L3B_EXP_SYNCS) && L3B_EXP_SYNCS == 2
+#define L3B_PHASE_SYNC1() __syncwarp()
+#define L3B_PHASE_SYNC2() __syncthreads()
+#else
+#define L3B_PHASE_SYNC1() __syncthreads()
+#define L3B_PHASE_SYNC2() __syncthreads()
+#endif
 
 template <int NCH, bool FUSED> struct VT;
 template <bool FUSED> struct VT<1, FUSED> {
@@ -723,7 +737,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 }
             }
         }
-        L3B_PHASE_SYNC();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
+        L3B_PHASE_SYNC1();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
 
         // ---------------- reorder + antialias + IMDCT + frequency inversion (minimp3.d:1215-1229) ----------
         if (!L12 && act) {
@@ -807,7 +821,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 }
             }
         }
-        L3B_PHASE_SYNC();
+        L3B_PHASE_SYNC2();
 
         // ---------------- DCT-32 matrixing across bands, one time slot per lane (minimp3.d:1232-1298) -------
         if (act && mode >= 1 && lane < NS) {

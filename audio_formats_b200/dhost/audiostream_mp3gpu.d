@@ -52,6 +52,20 @@ nothrow @nogc:
         return true;
     }
 
+    /// The same through the reference's own I/O thunks (mp3_io_read / mp3_io_seek, stream.d:2243-2254, over IOCallbacks,
+    /// io.d:16-26): what startDecoding passes to mp3dec_ex_open_cb today (stream.d:1728) goes to the library unchanged;
+    /// the library drains the callbacks into memory itself (it decodes ahead in large windows and seeks freely).
+    bool openCallbacks(l3b_read_cb readThunk, l3b_seek_cb seekThunk, void* decoderContext,
+                       out float sampleRate, out int numChannels, out long lengthInFrames)
+    {
+        if (!g_mp3gpu.ensure()) return false;
+        if (l3b_stream_open_callbacks(g_mp3gpu.ctx, readThunk, seekThunk, decoderContext, &handle) != L3B_OK) return false;
+        sampleRate = l3b_stream_samplerate(handle);
+        numChannels = l3b_stream_num_channels(handle);
+        lengthInFrames = l3b_stream_length_frames(handle);
+        return true;
+    }
+
     /// stream.d:537-551
     int readSamplesFloat(float* outData, int frames) { return l3b_stream_read_float(handle, outData, frames); }
 
@@ -109,4 +123,42 @@ int mp3BatchLengths(const(ubyte)[][] files, ulong[] samples, int[] channels, int
         l3b_scan_free(s);
     }
     return L3B_OK;
+}
+
+/// The throughput path: many in-memory files -> PCM in one (ideally page-locked: l3b_host_alloc_near) buffer, pipelined in
+/// waves over one or more GPUs inside the library (prepass threads, per-GPU lanes, blocking waits).  `s16` selects 16-bit
+/// delivery (the un-dithered conversion of wav.d:475-700), which halves the device -> host traffic that bounds the path.
+/// results[i] tells where stream i landed (element offset, frames, channels, rate) or why it could not be decoded.
+struct Mp3BatchPipeline
+{
+nothrow @nogc:
+    l3b_pipeline_t* handle;
+
+    bool open(const(int)[] devices, bool s16 = true, int lanes = 4, int waveStreams = 16)
+    {
+        l3b_pipeline_opts_t o;
+        o.lanes = lanes; o.wave_streams = waveStreams; o.scan_threads = 0; o.flags = s16 ? L3B_OUT_S16 : 0;
+        return l3b_pipeline_create(devices.ptr, cast(int) devices.length, &o, &handle) == L3B_OK;
+    }
+
+    int decode(const(ubyte*)[] data, const(size_t)[] sizes, void* outPcm, ulong capacityElems, l3b_stream_result_t[] results)
+    {
+        ulong used;
+        return l3b_pipeline_decode(handle, data.ptr, sizes.ptr, cast(uint) data.length, outPcm, capacityElems, results.ptr, &used);
+    }
+
+    void close() { if (handle !is null) l3b_pipeline_destroy(handle); handle = null; }
+}
+
+/// Batch decode with the prepass on the GPU as well (frame walk, side info, reservoir, main-data gather as kernels for
+/// well-formed files; anything else takes the host prepass inside the same call).
+int decodeMP3BatchRaw(const(ubyte*)[] data, const(size_t)[] sizes, void*[] outPcm, bool s16 = false, int device = 0)
+{
+    if (!g_mp3gpu.ensure(device)) return L3B_E_NOGPU;
+    l3b_raw_t* raw;
+    int rc = l3b_raw_open(g_mp3gpu.ctx, data.ptr, sizes.ptr, cast(uint) data.length, s16 ? L3B_OUT_S16 : 0, &raw);
+    if (rc != L3B_OK) return rc;
+    scope(exit) l3b_raw_free(raw);
+    // the caller sizes outPcm[i] from l3b_raw_samples(raw, i) in a real host; here they are assumed large enough
+    return l3b_raw_decode(raw, outPcm.ptr);
 }

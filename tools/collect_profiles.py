@@ -3,7 +3,7 @@
     python tools/collect_profiles.py r01b"""
 import csv, json, shutil, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01b"
-for f in ("bench_ours.json", "bench_reference.json", "launches_bench.csv", "fp32_pipes.txt"):
+for f in ("bench_ours.json", "bench_reference.json", "launches_bench.csv", "fp32_pipes.txt", "dct32_tc.txt"):
     shutil.copy(f"gpurun_out/{tag}_{f}", f"profiles/{tag}_{f}")
 subprocess.run([sys.executable, "tools/summarize_ncu.py", f"gpurun_out/{tag}_kernels.ncu-rep", f"profiles/{tag}_kernels_ncu_summary.txt"],
                stdout=subprocess.DEVNULL, check=True)
@@ -26,6 +26,16 @@ json.dump(out, open(f"profiles/{tag}_traffic.json", "w"), indent=1)
 d = json.load(open(f"profiles/{tag}_bench_ours.json"))
 r = d["roofline"]; e = d["e2e"]
 print("value", round(d["value"]), "ms/step", round(d["ms_per_step"], 2), "granule", round(r["ms_per_launch"], 2), "entropy", round(r["entropy_kernels_ms"], 2))
-print("e2e", round(e["value"]), round(e["ms_per_step"], 1), "ms", round(e.get("d2h_achieved_gbs", 0), 1), "of", round(e.get("d2h_pinned_peak_gbs", 0), 1), "GB/s")
+print("e2e", round(e["value"]), round(e["ms_per_step"], 1), "ms", round(e.get("d2h_achieved_gbs", 0), 1), "of", round(e.get("d2h_concurrent_peak_gbs") or 0, 1), "GB/s")
+import os
+if os.path.exists(f"gpurun_out/{tag}_granule_fused.ncu-rep"):
+    subprocess.run([sys.executable, "tools/summarize_ncu.py", f"gpurun_out/{tag}_granule_fused.ncu-rep", f"profiles/{tag}_granule_fused_ncu_summary.txt"],
+                   stdout=subprocess.DEVNULL, check=True)
+alg = r["hbm"]["algorithmic_bytes_per_launch"]
+tot = sum(v["traffic"] for v in out.values())
+print("traffic / algorithmic bytes: granule", round(out["granule"]["traffic"] / alg, 3), "whole step", round(tot / alg, 3))
+out["_summary"] = {"algorithmic_bytes_per_step": alg, "granule_traffic_over_algorithmic": out["granule"]["traffic"] / alg,
+                   "step_traffic_over_algorithmic": tot / alg}
+json.dump(out, open(f"profiles/{tag}_traffic.json", "w"), indent=1)
 print("cpu", round(d["cpu_baseline"]["value"]), "ref arm", round(json.load(open(f"profiles/{tag}_bench_reference.json"))["value"]))
-print({k: (round(v["traffic"] / 1e9, 2), v["duration_under_ncu"]) for k, v in out.items()})
+print({k: (round(v["traffic"] / 1e9, 2), v["duration_under_ncu"]) for k, v in out.items() if not k.startswith("_")})
