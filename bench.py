@@ -238,11 +238,13 @@ class Join:
             self.dist.destroy_process_group()
 
 
-def d2h_rate_gbs(torch, join, dst=None, reps=2):
+def d2h_rate_gbs(torch, join, dst=None, reps=2, h2d_fraction=0.0):
     """Device -> pinned host copy rate of this box, all ranks AT THE SAME TIME between two barriers (per-rank rate of the
     slowest rank): the ceiling of any end-to-end number that delivers PCM to the host.  `dst` (a pinned numpy array, the
     pipeline's own output buffer) makes it a copy of up to 8 GiB into DISTINCT host pages, 1 GiB at a time, like the
-    pipeline's deliveries; a 1 GiB copy repeated into one buffer partly lands in the CPU's last-level cache and reads high."""
+    pipeline's deliveries; a 1 GiB copy repeated into one buffer partly lands in the CPU's last-level cache and reads high.
+    h2d_fraction > 0: a host -> device copy of that fraction of the bytes runs on a second stream at the same time, like the
+    pipeline's uploads of the bitstreams (the two directions share the host's side of the link)."""
     try:
         chunk = 1 << 28   # floats: 1 GiB
         src = torch.empty(chunk, dtype=torch.float32, device="cuda")
@@ -252,12 +254,19 @@ def d2h_rate_gbs(torch, join, dst=None, reps=2):
         else:
             host = torch.from_numpy(dst.view(np.float32))
             n_chunks = max(1, min(8, host.numel() // chunk))
+        up_n = int(chunk * h2d_fraction)
+        up_host = torch.empty(max(1, up_n), dtype=torch.float32).pin_memory() if up_n else None
+        up_dev = torch.empty(max(1, up_n), dtype=torch.float32, device="cuda") if up_n else None
+        side = torch.cuda.Stream() if up_n else None
         best = 0.0
         for _ in range(reps):
             join.barrier()
             c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             c0.record()
             for k in range(n_chunks):
+                if up_n:
+                    with torch.cuda.stream(side):
+                        up_dev.copy_(up_host, non_blocking=True)
                 host[k * chunk:(k + 1) * chunk].copy_(src, non_blocking=True)
             c1.record()
             torch.cuda.synchronize()
@@ -288,7 +297,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=None, help="streams per GPU (default: the configuration's size)")
     ap.add_argument("--seconds", type=float, default=None, help="seconds per stream (default: the configuration's)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-lanes", type=int, default=4)
     ap.add_argument("--e2e-wave", type=int, default=16, help="streams per pipeline wave")
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
@@ -528,6 +537,7 @@ def main():
         parity["crc_compare"] = "crc32 of every stream's float PCM: device-resident run vs the wave pipeline's decode"
         d2h16 = hb.pcm_floats * 2
         peak = d2h_rate_gbs(torch, join, out_f32)
+        peak_mixed = d2h_rate_gbs(torch, join, out_f32, h2d_fraction=h2d / d2h16)
         e2e = {"value": total_audio / sec16, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h16,
                "ms_per_step": sec16 * 1e3, "steps": args.e2e_steps, "output": "int16 PCM in pinned host memory (L3B_OUT_S16)",
                "pipeline": {"lanes": args.e2e_lanes, "wave_streams": args.e2e_wave, "scan_threads": threads,
@@ -536,8 +546,11 @@ def main():
                "d2h_achieved_gbs": d2h16 / sec16 / 1e9,
                "d2h_concurrent_peak_gbs": peak, "d2h_concurrent_peak_aggregate_gbs": None if peak is None else peak * world,
                "d2h_frac_of_concurrent_peak": None if not peak else d2h16 / sec16 / 1e9 / peak,
+               "d2h_concurrent_peak_with_uploads_gbs": peak_mixed,
+               "d2h_frac_of_concurrent_peak_with_uploads": None if not peak_mixed else d2h16 / sec16 / 1e9 / peak_mixed,
                "d2h_peak_note": "up to 8 x 1 GiB device->pinned copies into distinct pages of the output buffer, every rank at the same time "
-                                "between two barriers, slowest rank, best of 2",
+                                "between two barriers, slowest rank, best of 2; `with_uploads`: the same while a host->device copy of "
+                                "h2d_bytes_per_step / d2h_bytes_per_step of the bytes runs on a second stream, like the pipeline's uploads",
                "f32": {"value": total_audio / sec32, "ms_per_step": sec32 * 1e3, "d2h_bytes_per_step": pcm_bytes,
                        "d2h_achieved_gbs": pcm_bytes / sec32 / 1e9, "output": "float PCM in pinned host memory",
                        "seconds_per_step_by_phase_summed_over_threads": prof32}}

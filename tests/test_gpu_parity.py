@@ -209,6 +209,33 @@ def test_fused_math_mode_is_within_tolerance(ctx, cfg):
     assert ident >= FUSED_MIN_IDENTICAL, ident
 
 
+def test_documented_deviation_huffman_overrun_past_the_frame(ctx):
+    """DESIGN.md 6, deviation (i), shown AS a deviation.  A (malformed) granule-channel whose big_values region runs past
+    the end of its frame's main data: the reference's per-frame buffer is zero there (D default initialisation of the
+    scratch), the linear blob of the GPU path holds the next frame's bytes.  Both decode the stream without complaint and
+    agree everywhere except around the damaged granule -- and there they do differ, which is what the document says."""
+    import audio_formats_b200 as af
+    import oracle
+    from audio_formats_b200 import synth
+    st = synth.generate(synth.SynthParams(seed=77, nframes=60, reservoir=0, no_padding=1))     # 417-byte frames, main_data_begin = 0
+    b = bytearray(st.data)
+    k = 30                                       # frame to damage: big_values of its LAST granule-channel -> 288 pairs
+    bit0 = (417 * k + 4) * 8 + 20 + 3 * 59 + 12  # MPEG-1 stereo side info: 20 bits, then 59 per granule-channel; part2_3_length is 12 bits
+    for i in range(9):
+        byte, bit = (bit0 + i) >> 3, 7 - ((bit0 + i) & 7)
+        want = (288 >> (8 - i)) & 1
+        b[byte] = (b[byte] & ~(1 << bit)) | (want << bit)
+    data = bytes(b)
+    ref, _ = oracle.decode_all(data)
+    (got,) = ctx.decode([data])
+    assert got.shape == ref.shape == (60 * 1152, 2)
+    g = 2 * k + 1                                # the damaged granule
+    lo, hi = 576 * g, 576 * (g + 3)              # its own PCM, the next granule (IMDCT overlap) and the one after (synthesis history)
+    same = got.view(np.uint32) == ref.view(np.uint32)
+    assert same[:lo].all() and same[hi:].all()
+    assert not same[lo:hi].all(), "the over-read no longer differs from the reference: update DESIGN.md section 6 (i)"
+
+
 def test_config5_320kbps(ctx):
     from audio_formats_b200 import synth
     check_stream(ctx, synth.generate(synth.config5_params(5, 6.0), want_quantised=True), "config5")
