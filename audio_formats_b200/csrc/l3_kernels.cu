@@ -337,16 +337,12 @@ struct __align__(16) WarpSmem {
     // granule.  The current-granule rows ALIAS the spectrum buffer `xr` (natural layout while requantising,
     // x19 padded layout between IMDCT and DCT): each stage has consumed its input before the next one writes.
     typename VT<NCH, false>::T Dbuf[1 + 15 * kDStride + kXrStride];  // D = Dbuf + 1, so that row 15 (= xr) is 16-byte aligned
-#ifndef L3B_EXP_20W
     uint4 st_is[NCH * kIsChunks];              // TMA-staged inputs of the next granule: quantised spectra (only the chunks
                                                //   that hold anything: `nz_chunks` of each channel),
-#endif
     uint4 st_rec[NCH * kSfRecBytes / 16];      //   scalefactor records,
     uint4 st_desc[NCH];                        //   descriptors
     float gains[NCH][40];                      // band gains of this granule (minimp3.d:714-719)
-#ifndef L3B_EXP_20W
     uint8_t sfbpair[3][288];
-#endif
     uint8_t ist[40];
     uint8_t smode[40];
     float kl[40], kr[40];
@@ -384,13 +380,8 @@ constexpr int kCtaTableBytes = 1040 + 496 + 2048;   // s_pow43 (257 floats + pad
 
 // L12: the Layer I / II instance -- a granule is 12 slots x 32 subbands whose samples arrive dequantised and scaled from
 // l12_parse_kernel (p.l12_x); only the synthesis half of the pipeline runs (minimp3.d:1567 calls mp3d_synth_granule with 12).
-#ifdef L3B_EXP_20W
-#define L3B_WARPS_PER_SM 20
-#else
-#define L3B_WARPS_PER_SM 16
-#endif
 template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16, bool L12>
-__global__ void __launch_bounds__(32 * WARPS, L3B_WARPS_PER_SM / WARPS) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
+__global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(BatchParams p, const Tile* tiles, uint32_t n_tiles) {
     typedef VT<NCH, FUSED> V;
     typedef typename V::T T;
     constexpr int NS = L12 ? 12 : 18;   // time slots per granule
@@ -417,14 +408,8 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_WARPS_PER_SM / WARPS) l3_granu
     const bool mpeg1 = S.mpeg1 != 0;
     const int row = S.sr_idx;
 
-#ifdef L3B_EXP_20W   // experiment: 20 warps per SM -- no spectra staging, band map read through L1, 96 registers
-    const uint8_t* const sfb_of_pair = p.t.sfb_of_pair + row * 3 * 288;
-#define L3B_SFBPAIR(kind, i) __ldg(sfb_of_pair + (kind) * 288 + (i))
-#else
     for (int i = lane; i < 3 * 288 / 4; i += 32)
         reinterpret_cast<uint32_t*>(&W.sfbpair[0][0])[i] = reinterpret_cast<const uint32_t*>(p.t.sfb_of_pair + row * 3 * 288)[i];
-#define L3B_SFBPAIR(kind, i) W.sfbpair[kind][i]
-#endif
     for (int i = lane; i < 15 * kDStride; i += 32) D[i] = V::zero();
     for (int i = lane; i < 40; i += 32) W.ist[i] = 0;
     if (lane == 0) mbar_init(&W.mbar, 1);
@@ -476,16 +461,9 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_WARPS_PER_SM / WARPS) l3_granu
     // hold anything are fetched: n0 / n1 = nz_chunks of the two channels (from p.nzc, read a granule ahead).
     auto prefetch = [&](int g, uint32_t n0, uint32_t n1) {
         const uint64_t di = S.first_grch + (uint64_t)g * NCH;
-#ifdef L3B_EXP_20W
-        mbar_expect_tx(&W.mbar, NCH * (kSfRecBytes + 16));
-        // the spectra are read straight from global memory: bring the rows of this granule into L2 meanwhile
-        for (uint32_t q = 0; q < n0; q += 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.is + di * kIsChunks + q));
-        if (NCH == 2) for (uint32_t q = 0; q < n1; q += 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.is + (di + 1) * kIsChunks + q));
-#else
         mbar_expect_tx(&W.mbar, (n0 + n1) * 16u + NCH * (kSfRecBytes + 16));
         if (n0) tma_load_1d(W.st_is, p.is + di * kIsChunks, n0 * 16u, &W.mbar);
         if (NCH == 2 && n1) tma_load_1d(W.st_is + kIsChunks, p.is + (di + 1) * kIsChunks, n1 * 16u, &W.mbar);
-#endif
         tma_load_1d(W.st_rec, p.sf + di * kSfRecBytes, NCH * kSfRecBytes, &W.mbar);
         tma_load_1d(W.st_desc, p.grch + di, NCH * 16, &W.mbar);
     };
@@ -586,11 +564,7 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_WARPS_PER_SM / WARPS) l3_granu
             {
                 const int nch0 = *reinterpret_cast<const uint16_t*>(rec0 + 80);
                 const int nch1 = *reinterpret_cast<const uint16_t*>(rec1 + 80);
-#ifdef L3B_EXP_20W
-                const uint32_t* isw0 = reinterpret_cast<const uint32_t*>(p.is + di * kIsChunks);
-#else
                 const uint32_t* isw0 = reinterpret_cast<const uint32_t*>(W.st_is);
-#endif
                 const uint32_t* isw1 = isw0 + (NCH - 1) * (kIsChunks * 4);
                 const bool ms_now = NCH == 2 && ms_frame && !istereo;
                 const int nz_hi = max(nch0, NCH == 2 ? nch1 : 0);   // chunks (8 coefficients) holding anything non-zero
@@ -602,15 +576,6 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_WARPS_PER_SM / WARPS) l3_granu
                 // lands somewhere inside the table (and is redone below)
                 const char* const tab = reinterpret_cast<const char*>(s_pow43);
                 uint32_t bigmask = 0;
-#ifdef L3B_EXP_20W
-                uint32_t gva[9], gvb[9];   // all loads in flight at once (the rows were prefetched into L2 a granule ago)
-#pragma unroll
-                for (int m = 0; m < 9; m++) {
-                    const int pi = lane + 32 * m;
-                    gva[m] = (pi >> 2) < nch0 ? __ldg(isw0 + pi) : 0u;
-                    gvb[m] = (NCH == 2 && (pi >> 2) < nch1) ? __ldg(isw1 + pi) : 0u;
-                }
-#endif
 #pragma unroll
                 for (int m = 0; m < 9; m++) {
                     const int pi = lane + 32 * m;
@@ -621,14 +586,10 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_WARPS_PER_SM / WARPS) l3_granu
                             for (int c = 0; c < NCH; c++) p.tap_xr[(di + c) * 576 + 2 * pi] = p.tap_xr[(di + c) * 576 + 2 * pi + 1] = 0.0f;
                         continue;
                     }
-#ifdef L3B_EXP_20W
-                    const uint32_t va = gva[m], vb = gvb[m];
-#else
                     const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;   // chunks past nz_chunks were never fetched
                     const uint32_t vb = (NCH == 2 && (pi >> 2) < nch1) ? isw1[pi] : 0u;
-#endif
-                    const float sa = scf0[L3B_SFBPAIR(kind0, pi)];
-                    const float sb = NCH == 2 ? scf1[L3B_SFBPAIR(kind1, pi)] : 0.0f;
+                    const float sa = scf0[W.sfbpair[kind0][pi]];
+                    const float sb = NCH == 2 ? scf1[W.sfbpair[kind1][pi]] : 0.0f;
                     // a 16-bit value lies in [-128, 127] iff its bits 15..7 are all equal
                     const uint32_t wide = ((va ^ (va << 1)) | (vb ^ (vb << 1))) & 0xFF00FF00u;
                     bigmask |= (wide ? 1u : 0u) << m;
@@ -658,12 +619,12 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_WARPS_PER_SM / WARPS) l3_granu
                         if (!((bigmask >> m) & 1u)) continue;
                         const int pi = lane + 32 * m;
                         const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;
-                        const float sa = scf0[L3B_SFBPAIR(kind0, pi)];
+                        const float sa = scf0[W.sfbpair[kind0][pi]];
                         float a0 = requant(s_pow43, (int)(int16_t)(va & 0xFFFFu), sa);
                         float a1 = requant(s_pow43, (int)(int16_t)(va >> 16), sa);
                         if (NCH == 2) {
                             const uint32_t vb = (pi >> 2) < nch1 ? isw1[pi] : 0u;
-                            const float sb = scf1[L3B_SFBPAIR(kind1, pi)];
+                            const float sb = scf1[W.sfbpair[kind1][pi]];
                             float b0 = requant(s_pow43, (int)(int16_t)(vb & 0xFFFFu), sb);
                             float b1 = requant(s_pow43, (int)(int16_t)(vb >> 16), sb);
                             if (TAPS && mode == 2) {
@@ -748,7 +709,7 @@ __global__ void __launch_bounds__(32 * WARPS, L3B_WARPS_PER_SM / WARPS) l3_granu
                 __syncwarp();
                 for (int m = 0; m < 18; m++) {
                     const int k = lane + 32 * m;
-                    const int sfb = L3B_SFBPAIR(kind0, k >> 1);
+                    const int sfb = W.sfbpair[kind0][k >> 1];
                     const int md = W.smode[sfb];
                     const float2 v = X[k];
                     if (md == 1) X[k] = make_float2(__fmul_rn(v.x, W.kl[sfb]), __fmul_rn(v.x, W.kr[sfb]));
