@@ -56,21 +56,13 @@ void upload_constants() {
 //   FUSED = true   tolerance mode: multiply-adds of the reference are contracted into FFMA2 by hand (one rounding
 //                  instead of two).  Not bit-identical; measured against the north star's 1e-5 FS / 99.99 % bar.
 
-// The warps of a CTA run the stages in lockstep (every warp owns its buffers; the barriers are there for instruction-cache
-// locality only).  L3B_EXP_SYNCS: A/B builds -- 0 none, 1 only the first, 2 only the second.
-#if defined(L3B_EXP_SYNCS) && L3B_EXP_SYNCS == 0
-#define L3B_PHASE_SYNC1() __syncwarp()
-#define L3B_PHASE_SYNC2() __syncwarp()
-#elif defined(L3B_EXP_SYNCS) && L3B_EXP_SYNCS == 1
-#define L3B_PHASE_SYNC1() __syncthreads()
-#define L3B_PHASE_SYNC2() __syncwarp()
-#elif defined(L3B_EXP_SYNCS) && L3B_EXP_SYNCS == 2
-#define L3B_PHASE_SYNC1() __syncwarp()
-#define L3B_PHASE_SYNC2() __syncthreads()
-#else
-#define L3B_PHASE_SYNC1() __syncthreads()
-#define L3B_PHASE_SYNC2() __syncthreads()
+#ifndef L3B_RQ_UNROLL
+#define L3B_RQ_UNROLL 1
 #endif
+// Unroll factor of the requantisation loop (9 trips).  Rolled: the loop of a granule must stay inside the 32 KB instruction
+// cache that the 16 warps of an SM share (measured: unrolled 19.3 ms, rolled 18.9 ms, and only then do the phase barriers
+// that round 1 needed stop paying).
+constexpr int kRqUnroll = L3B_RQ_UNROLL;
 
 template <int NCH, bool FUSED> struct VT;
 template <bool FUSED> struct VT<1, FUSED> {
@@ -91,9 +83,6 @@ template <bool FUSED> struct VT<1, FUSED> {
     static __device__ __forceinline__ T mm_sub(T a, float wa, T b, float wb) {
         return FUSED ? __fmaf_rn(-b, wb, __fmul_rn(a, wa)) : __fsub_rn(__fmul_rn(a, wa), __fmul_rn(b, wb));
     }
-    // the same with one weight per channel
-    static __device__ __forceinline__ T mmw_add(T a, float wa0, float, T b, float wb0, float) { return mm_add(a, wa0, b, wb0); }
-    static __device__ __forceinline__ T mmw_sub(T a, float wa0, float, T b, float wb0, float) { return mm_sub(a, wa0, b, wb0); }
     static __device__ __forceinline__ T shfl_up(T a) { return __shfl_up_sync(0xffffffffu, a, 1); }
     static __device__ __forceinline__ T shfl_down(T a) { return __shfl_down_sync(0xffffffffu, a, 1); }
     static __device__ __forceinline__ T sel(bool c0, bool, T a, T b) { return c0 ? a : b; }
@@ -135,12 +124,6 @@ template <bool FUSED> struct VT<2, FUSED> {
     static __device__ __forceinline__ T mm_sub(T a, float wa, T b, float wb) {
         return FUSED ? __ffma2_rn(b, bc(-wb), muls(a, wa)) : add(muls(a, wa), muls(b, -wb));
     }
-    static __device__ __forceinline__ T mmw_add(T a, float wa0, float wa1, T b, float wb0, float wb1) {
-        return FUSED ? __ffma2_rn(b, make_float2(wb0, wb1), mulw(a, wa0, wa1)) : add(mulw(a, wa0, wa1), mulw(b, wb0, wb1));
-    }
-    static __device__ __forceinline__ T mmw_sub(T a, float wa0, float wa1, T b, float wb0, float wb1) {
-        return FUSED ? __ffma2_rn(b, make_float2(-wb0, -wb1), mulw(a, wa0, wa1)) : add(mulw(a, wa0, wa1), mulw(b, -wb0, -wb1));
-    }
     static __device__ __forceinline__ T shfl_up(T a) {
         return make_float2(__shfl_up_sync(0xffffffffu, a.x, 1), __shfl_up_sync(0xffffffffu, a.y, 1));
     }
@@ -165,21 +148,23 @@ __device__ __forceinline__ float ldexp_q2(float y, int exp_q2) {
     return y;
 }
 
+// one step of L3_ldexp_q2 for 0 <= e <= 120: g_expfrac[e & 3] * (float)((1 << 30) >> (e >> 2)); the second factor is a power of two
+__device__ __forceinline__ float ldexp_step(int e) { return __fmul_rn(c_expfrac[e & 3], __int_as_float((127 + 30 - (e >> 2)) << 23)); }
+
 // L3_pow_43 for x >= 129 (minimp3.d:737-745)
 __device__ __noinline__ float pow43_big(const float* pow43, int x) {
     int mult = 256;
     if (x < 1024) { mult = 16; x <<= 3; }
     int sign = 2 * x & 64;
     float frac = __fdiv_rn((float)((x & 63) - sign), (float)((x & ~63) + sign));
-    return pow43[(x + sign) >> 6] * (1.0f + frac * ((4.0f / 3) + frac * (2.0f / 9))) * (float)mult;
+    return __ldg(pow43 + ((x + sign) >> 6)) * (1.0f + frac * ((4.0f / 3) + frac * (2.0f / 9))) * (float)mult;
 }
 
-// s_pow43s[v + 128] = sign(v) * |v|^(4/3) for -128 <= v <= 128: the reference's own trick of a mirrored table
-// (minimp3.d:722-725, 816), extended to the whole table range.  (-p)*s == -(p*s) exactly.
-__device__ __forceinline__ float requant(const float* pow43s, int v, float s) {
-    if ((unsigned)(v + 128) <= 256u) return __fmul_rn(pow43s[v + 128], s);
-    int a = v < 0 ? -v : v;
-    float r = __fmul_rn(pow43_big(pow43s + 128, a), s);
+// General path (a value outside the 9-bit range of the shared table somewhere in the lane's words): |v|^(4/3) from the positive table in global memory
+// (129 entries, minimp3.d:722-725) or L3_pow_43's interpolation, then the sign.  (-p)*s == -(p*s) exactly.
+__device__ __forceinline__ float requant(const float* pow43g, int v, float s) {
+    const int a = v < 0 ? -v : v;
+    const float r = __fmul_rn(a <= 128 ? __ldg(pow43g + a) : pow43_big(pow43g, a), s);
     return v < 0 ? -r : r;
 }
 
@@ -224,9 +209,11 @@ __device__ __forceinline__ void dct3_9(typename V::T* y) {
     y[8] = V::add(s4, s7);
 }
 
-// L3_imdct36 for one band (minimp3.d:1062-1100).  ws0/ws1: window row (0 normal, 1 stop) per channel.
+// L3_imdct36 for one band (minimp3.d:1062-1100).  wrow = 18 * window row (0 normal, 1 stop), the same for every channel in T
+// (a granule whose channels need different rows goes through imdct_split): the weights are scalars, broadcast by the packed
+// multiply itself.
 template <class V>
-__device__ __forceinline__ void imdct36_band(const typename V::T* x, typename V::T* ovl, int ws0, int ws1, typename V::T* out) {
+__device__ __forceinline__ void imdct36_band(const typename V::T* x, typename V::T* ovl, int wrow, typename V::T* out) {
     typedef typename V::T T;
     T co[9], si[9];
     co[0] = V::neg(x[0]);
@@ -244,15 +231,14 @@ __device__ __forceinline__ void imdct36_band(const typename V::T* x, typename V:
     si[3] = V::neg(si[3]);
     si[5] = V::neg(si[5]);
     si[7] = V::neg(si[7]);
-    const float* wa = c_mdctw + 18 * ws0;
-    const float* wb = c_mdctw + 18 * ws1;
+    const float* w = c_mdctw + wrow;
 #pragma unroll
     for (int i = 0; i < 9; i++) {
         T o = ovl[i];
         T sum = V::mm_add(co[i], c_twid9[9 + i], si[i], c_twid9[0 + i]);
         ovl[i] = V::mm_sub(co[i], c_twid9[0 + i], si[i], c_twid9[9 + i]);
-        out[i] = V::mmw_sub(o, wa[0 + i], wb[0 + i], sum, wa[9 + i], wb[9 + i]);
-        out[17 - i] = V::mmw_add(o, wa[9 + i], wb[9 + i], sum, wa[0 + i], wb[0 + i]);
+        out[i] = V::mm_sub(o, w[0 + i], sum, w[9 + i]);
+        out[17 - i] = V::mm_add(o, w[9 + i], sum, w[0 + i]);
     }
 }
 
@@ -297,9 +283,6 @@ __device__ __forceinline__ void imdct_short_band(const typename V::T* x, typenam
 }
 
 constexpr int kDStride = 33;  // T elements per row (odd: the DCT's per-slot column writes hit distinct banks)
-// a tile's own granules + the recompute halo: two granules, three when the halo would otherwise start on the second
-// granule of an intensity-stereo frame (whose intensity positions are per-FRAME scratch, see below)
-constexpr int kMaxIter = kTileGranules + 3;
 
 // ---- mbarrier + TMA (1-D bulk copy) helpers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -328,8 +311,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 32-bit load through a shared-window address (register + constant; a generic pointer to a static table would have its
+// cluster-window base re-derived and added in front of every use)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // per-warp shared memory
 template <int NCH>
 struct __align__(16) WarpSmem {
@@ -341,13 +330,123 @@ struct __align__(16) WarpSmem {
                                                //   that hold anything: `nz_chunks` of each channel),
     uint4 st_rec[NCH * kSfRecBytes / 16];      //   scalefactor records,
     uint4 st_desc[NCH];                        //   descriptors
-    float gains[NCH][40];                      // band gains of this granule (minimp3.d:714-719)
+    float gains[40][NCH];                      // band gains of this granule (minimp3.d:714-719), the channels of a band adjacent
     uint8_t sfbpair[3][288];
     uint8_t ist[40];
     uint8_t smode[40];
     float kl[40], kr[40];
     uint64_t mbar;
+    // delivery window of the tile (see the kernel): read back once per granule by the window stage, parked here rather than
+    // in registers (the allocator would spill them to local memory, which misses L1 with the shared-memory carve-out at its
+    // maximum)
+    char* tbase;
+    int rel_lo0, rel_hi0;
+    int kstart, kend;   // first halo granule / end of the tile, relative to the tile's first granule (same reason)
 };
+
+// L3_intensity_stereo (minimp3.d:898-982) on channel 0's band layout, for the whole warp; X = the granule's spectrum (natural
+// order, both channels).  Out of line on purpose: see the call.
+__device__ __noinline__ void intensity_stereo(WarpSmem<2>& W, float2* X, int kind0, bool mpeg1, int hb, int mpeg2_sh, const uint8_t* sfbw,
+                                              const uint16_t* sfbo, int lane) {
+    const int n_long_sfb0 = kind0 == 0 ? 22 : (kind0 == 1 ? 0 : (mpeg1 ? 8 : 6));
+    const int n_sfb0 = n_long_sfb0 + (kind0 == 0 ? 0 : (kind0 == 1 ? 39 : 30));
+    int mb0 = -1, mb1 = -1, mb2 = -1;
+    for (int i = lane; i < n_sfb0; i += 32) {  // L3_stereo_top_band
+        const int off = __ldg(sfbo + i), wdt = __ldg(sfbw + i);
+        bool nz = false;
+#pragma unroll 1
+        for (int k = 0; k < wdt; k++) nz |= (X[off + k].y != 0.0f);
+        if (nz) { int c = i % 3; if (c == 0) mb0 = max(mb0, i); else if (c == 1) mb1 = max(mb1, i); else mb2 = max(mb2, i); }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        mb0 = max(mb0, __shfl_xor_sync(0xffffffffu, mb0, sft));
+        mb1 = max(mb1, __shfl_xor_sync(0xffffffffu, mb1, sft));
+        mb2 = max(mb2, __shfl_xor_sync(0xffffffffu, mb2, sft));
+    }
+    if (n_long_sfb0) mb0 = mb1 = mb2 = max(max(mb0, mb1), mb2);
+    if (lane == 0) {
+        const int max_blocks = kind0 == 0 ? 1 : 3;
+        const int default_pos = mpeg1 ? 3 : 0;
+        const int mb[3] = {mb0, mb1, mb2};
+        for (int i = 0; i < max_blocks; i++) {
+            int itop = n_sfb0 - max_blocks + i, prev = itop - max_blocks;
+            W.ist[itop] = (uint8_t)(mb[i] >= prev ? default_pos : W.ist[prev]);
+        }
+    }
+    __syncwarp();
+    const unsigned max_pos = mpeg1 ? 7u : 64u;
+    for (int i = lane; i < n_sfb0; i += 32) {  // L3_stereo_process: per-sfb decision and gains
+        const unsigned ipos = W.ist[i];
+        const int mbc = (i % 3) == 0 ? mb0 : ((i % 3) == 1 ? mb1 : mb2);
+        uint8_t md = 0;
+        if (i > mbc && ipos < max_pos) {
+            float kl, kr, s = (hb & 2) ? 1.41421356f : 1.0f;
+            if (mpeg1) {
+                kl = c_pan[2 * ipos];
+                kr = c_pan[2 * ipos + 1];
+            } else {
+                kl = 1.0f;
+                kr = ldexp_q2(1.0f, (int)((ipos + 1) >> 1 << mpeg2_sh));
+                if (ipos & 1) { kl = kr; kr = 1.0f; }
+            }
+            W.kl[i] = kl * s;
+            W.kr[i] = kr * s;
+            md = 1;
+        } else if (hb & 2) {
+            md = 2;
+        }
+        W.smode[i] = md;
+    }
+    __syncwarp();
+#pragma unroll 2
+    for (int m = 0; m < 18; m++) {
+        const int k = lane + 32 * m;
+        const int sfb = W.sfbpair[kind0][k >> 1];
+        const int md = W.smode[sfb];
+        const float2 v = X[k];
+        if (md == 1) X[k] = make_float2(__fmul_rn(v.x, W.kl[sfb]), __fmul_rn(v.x, W.kr[sfb]));
+        else if (md == 2) X[k] = make_float2(__fadd_rn(v.x, v.y), __fsub_rn(v.x, v.y));
+    }
+    __syncwarp();
+}
+
+// Requantisation through the general path (minimp3.d:813-816, 737-745, 874-878 + MS stereo :885-896) for the trips of this
+// lane flagged in `bigmask`: a value outside the shared table's range.  tap_xr: the granule's row of the xr snapshot or null.
+template <int NCH, bool TAPS>
+__device__ __noinline__ void requant_wide(WarpSmem<NCH>& W, typename VT<NCH, false>::T* xr, const float* pow43g, uint32_t bigmask, int nch0, int nch1,
+                                          int kind0, int kind1, bool ms_now, int lane, float* tap_xr) {
+    const uint32_t* isw0 = reinterpret_cast<const uint32_t*>(W.st_is);
+    const uint32_t* isw1 = isw0 + (NCH - 1) * (kIsChunks * 4);
+#pragma unroll 1
+    for (int m = 0; m < 9; m++) {
+        if (!((bigmask >> m) & 1u)) continue;
+        const int pi = lane + 32 * m;
+        const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;
+        const float sa = W.gains[W.sfbpair[kind0][pi]][0];
+        float a0 = requant(pow43g, (int)(int16_t)(va & 0xFFFFu), sa);
+        float a1 = requant(pow43g, (int)(int16_t)(va >> 16), sa);
+        if (NCH == 2) {
+            const uint32_t vb = (pi >> 2) < nch1 ? isw1[pi] : 0u;
+            const float sb = W.gains[W.sfbpair[kind1][pi]][NCH - 1];
+            float b0 = requant(pow43g, (int)(int16_t)(vb & 0xFFFFu), sb);
+            float b1 = requant(pow43g, (int)(int16_t)(vb >> 16), sb);
+            if (TAPS && tap_xr) {
+                tap_xr[2 * pi] = a0; tap_xr[2 * pi + 1] = a1;
+                tap_xr[576 + 2 * pi] = b0; tap_xr[576 + 2 * pi + 1] = b1;
+            }
+            if (ms_now) {
+                const float l0 = __fadd_rn(a0, b0), r0 = __fsub_rn(a0, b0);
+                const float l1 = __fadd_rn(a1, b1), r1 = __fsub_rn(a1, b1);
+                a0 = l0; b0 = r0; a1 = l1; b1 = r1;
+            }
+            *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(a0, b0, a1, b1);
+        } else {
+            if (TAPS && tap_xr) { tap_xr[2 * pi] = a0; tap_xr[2 * pi + 1] = a1; }
+            *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(a0, a1);
+        }
+    }
+}
 
 // The (rare) band where the two channels of a granule use different transforms: one channel at a time.
 template <bool FUSED>
@@ -361,7 +460,7 @@ __device__ __noinline__ void imdct_split(float2* x, float2* ovl, float2* y, bool
 #pragma unroll
         for (int i = 0; i < 9; i++) os[i] = c ? ovl[i].y : ovl[i].x;
         if (c ? sh1 : sh0) imdct_short_band<V1>(xs, os, ys);
-        else imdct36_band<V1>(xs, os, c ? ws1 : ws0, 0, ys);
+        else imdct36_band<V1>(xs, os, 18 * (c ? ws1 : ws0), ys);
 #pragma unroll
         for (int i = 0; i < 18; i++) { if (c) y[i].y = ys[i]; else y[i].x = ys[i]; }
 #pragma unroll
@@ -373,10 +472,10 @@ template <bool FUSED>
 __device__ __noinline__ void imdct_split(float* x, float* ovl, float* y, bool sh0, bool, int ws0, int) {
     typedef VT<1, FUSED> V1;
     if (sh0) imdct_short_band<V1>(x, ovl, y);
-    else imdct36_band<V1>(x, ovl, ws0, 0, y);
+    else imdct36_band<V1>(x, ovl, 18 * ws0, y);
 }
 
-constexpr int kCtaTableBytes = 1040 + 496 + 2048;   // s_pow43 (257 floats + pad) | s_ldexp (121 floats + pad) | s_win (16 x 32 floats)
+constexpr int kCtaTableBytes = 2048 + 2048;   // s_pow43 (512 floats) | s_win (16 x 32 floats)
 
 // L12: the Layer I / II instance -- a granule is 12 slots x 32 subbands whose samples arrive dequantised and scaled from
 // l12_parse_kernel (p.l12_x); only the synthesis half of the pipeline runs (minimp3.d:1567 calls mp3d_synth_granule with 12).
@@ -386,20 +485,23 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
     typedef typename V::T T;
     constexpr int NS = L12 ? 12 : 18;   // time slots per granule
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    float* s_pow43 = reinterpret_cast<float*>(smem_raw);          // 257 signed entries (+pad), shared by the CTA
-    float* s_ldexp = reinterpret_cast<float*>(smem_raw + 1040);   // one step of L3_ldexp_q2: g_expfrac[e & 3] * 2^(30 - (e >> 2)), e <= 120
-    float* s_win = reinterpret_cast<float*>(smem_raw + 1040 + 496);   // synthesis window weights per lane: [tap k][w0 / w1][lane]
+    // tables shared by the CTA, statically allocated (their shared-memory addresses are compile-time constants, so a lookup
+    // is LDS [offset register + constant])
+    __shared__ __align__(16) float s_pow43[512];   // 512 signed entries
+    __shared__ __align__(16) float s_win[16 * 32];   // synthesis window weights per lane: [tap k][w0 / w1][lane]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem<NCH>& W = *reinterpret_cast<WarpSmem<NCH>*>(smem_raw + kCtaTableBytes + (size_t)warp * sizeof(WarpSmem<NCH>));
+    WarpSmem<NCH>& W = *reinterpret_cast<WarpSmem<NCH>*>(smem_raw + (size_t)warp * sizeof(WarpSmem<NCH>));
     T* const D = W.Dbuf + 1;
     T* const xr = D + 15 * kDStride;
 
-    for (int i = threadIdx.x; i < 257; i += 32 * WARPS) {
-        const float pw = p.t.pow43[i < 128 ? 128 - i : i - 128];
-        s_pow43[i] = i < 128 ? -pw : pw;
+    // s_pow43[v & 511] = sign(v) * |v|^(4/3) for -256 <= v <= 255: the reference's mirrored table (minimp3.d:722-725, 816)
+    // extended to a 9-bit range (table values up to 128, L3_pow_43's own interpolation above) and laid out so that the low
+    // nine bits of v are the index
+    for (int i = threadIdx.x; i < 512; i += 32 * WARPS) {
+        const int a = i < 256 ? i : 512 - i;
+        const float pw = a <= 128 ? __ldg(p.t.pow43 + a) : pow43_big(p.t.pow43, a);
+        s_pow43[i] = i < 256 ? pw : -pw;
     }
-    for (int i = threadIdx.x; i <= 120; i += 32 * WARPS)
-        s_ldexp[i] = __fmul_rn(c_expfrac[i & 3], __int_as_float((127 + 30 - (i >> 2)) << 23));   // both factors exact: (float)((1 << 30) >> (i >> 2))
 
     const uint32_t tile_idx = blockIdx.x * WARPS + warp;
     const bool have_tile = tile_idx < n_tiles;
@@ -445,7 +547,8 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
         const Desc ds = load_desc(p.grch + S.first_grch + (uint64_t)start * NCH);
         if (ds.second_granule() && !ds.reset_before() && (ds.hdr_bits() & 1)) start--;
     }
-    const int n_iter = have_tile ? (int)(tile.g0 + tile.ng) - start : 0;
+    // The granules of the tile are k = 0 .. ng-1; the halo is k = kstart .. -1 (two granules, three in the case above).
+    const int kstart = start - (int)tile.g0, kend = have_tile ? (int)tile.ng : kstart;
     T ovl[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) ovl[i] = V::zero();
@@ -453,47 +556,64 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
     __syncthreads();
 
     const int n_long_bands_mixed = 2 << (row == 1 ? 1 : 0);  // minimp3.d:1218
-    const uint64_t skipf = S.pcm_skip / NCH, countf = S.pcm_count / NCH;   // in frames
-    // delivery: float samples, or (S16) 16-bit ones at the same element offsets
-    char* const out_base = S16 ? reinterpret_cast<char*>(p.pcm16 + S.pcm_off) : reinterpret_cast<char*>(p.pcm + S.pcm_off);
+    // Delivery: float samples, or (S16) 16-bit ones at the same element offsets.  Frames [skip, skip + count) of the decoded
+    // signal are delivered; relative to the tile's first granule that is [r0, r0 + count), kept as two 32-bit numbers clamped
+    // far outside the tile (a tile spans 64 * 576 frames), and tbase points at frame 0 of granule g0 in the delivered signal
+    // (only ever dereferenced for delivered frames).
+    constexpr long long kGranFrames = 32 * NS;   // 576 (Layer III) / 384 (Layer I / II)
+    constexpr int kFrameBytes = NCH * (S16 ? 2 : 4);
+    const long long r0 = (long long)(S.pcm_skip / NCH) - (long long)tile.g0 * kGranFrames;
+    if (lane == 0) {
+        W.kstart = kstart;
+        W.kend = kend;
+        W.rel_lo0 = (int)max(-(1ll << 30), min(1ll << 30, r0));
+        W.rel_hi0 = (int)max(-(1ll << 30), min(1ll << 30, r0 + (long long)(S.pcm_count / NCH)));
+        W.tbase = (S16 ? reinterpret_cast<char*>(p.pcm16 + S.pcm_off) : reinterpret_cast<char*>(p.pcm + S.pcm_off)) - r0 * kFrameBytes;
+    }
+    // descriptor index of granule k, channel 0 (a batch holds fewer than 2^32 granule-channels: l3b_batch_create checks)
+    const uint32_t di0 = (uint32_t)S.first_grch + (uint32_t)tile.g0 * NCH;
 
     // lane 0: TMA bulk copies of granule g's inputs into the staging buffers.  Only the chunks of the spectra that
     // hold anything are fetched: n0 / n1 = nz_chunks of the two channels (from p.nzc, read a granule ahead).
-    auto prefetch = [&](int g, uint32_t n0, uint32_t n1) {
-        const uint64_t di = S.first_grch + (uint64_t)g * NCH;
+    auto prefetch = [&](uint32_t di32, uint32_t n0, uint32_t n1) {
+        const uint64_t di = di32;
         mbar_expect_tx(&W.mbar, (n0 + n1) * 16u + NCH * (kSfRecBytes + 16));
         if (n0) tma_load_1d(W.st_is, p.is + di * kIsChunks, n0 * 16u, &W.mbar);
         if (NCH == 2 && n1) tma_load_1d(W.st_is + kIsChunks, p.is + (di + 1) * kIsChunks, n1 * 16u, &W.mbar);
         tma_load_1d(W.st_rec, p.sf + di * kSfRecBytes, NCH * kSfRecBytes, &W.mbar);
         tma_load_1d(W.st_desc, p.grch + di, NCH * 16, &W.mbar);
     };
-    auto load_nz = [&](int g, uint32_t& n0, uint32_t& n1) {
-        const uint8_t* q = p.nzc + S.first_grch + (uint64_t)g * NCH;
+    auto load_nz = [&](uint32_t di32, uint32_t& n0, uint32_t& n1) {
+        const uint8_t* q = p.nzc + di32;
         n0 = __ldg(q);
         n1 = NCH == 2 ? __ldg(q + 1) : 0u;
     };
-    uint32_t nzn0 = 0, nzn1 = 0;   // lane 0: nz_chunks of the NEXT granule
-    if (!L12 && lane == 0 && n_iter > 0) {
-        load_nz(start, nzn0, nzn1);
-        prefetch(start, nzn0, nzn1);
+    uint32_t nzn0 = 0, nzn1 = 0;   // nz_chunks of the NEXT granule
+    if (!L12 && lane == 0 && kstart < kend) {
+        // The staging barrier's phase parity is k & 1: a tile whose first iteration is odd completes one empty phase first
+        // (the barrier expects one arrival per phase; nothing is in flight yet).
+        if (kstart & 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&W.mbar)) : "memory");
+        load_nz(di0 + kstart * NCH, nzn0, nzn1);
+        prefetch(di0 + kstart * NCH, nzn0, nzn1);
     }
-
-    for (int it = 0; it < kMaxIter; it++) {
-        const bool act = it < n_iter;
-        const int g = start + it;
+    __syncwarp();
+#pragma unroll 1
+    for (int k = kstart; k < W.kend; k++) {
+        const uint32_t phase = k & 1;
         // 2: a granule of the tile; 1: halo granule whose DCT outputs are history for the window; 0: halo granule that only
         // contributes IMDCT overlap.  Layer I / II: 12 slots per granule, so the 15 history slots span both halo granules.
-        const int mode = g >= (int)tile.g0 ? 2 : ((L12 || g == (int)tile.g0 - 1) ? 1 : 0);
-        const uint64_t di = S.first_grch + (uint64_t)g * NCH;
+        const int mode = k >= 0 ? 2 : ((L12 || k == -1) ? 1 : 0);
+        const uint32_t di32 = di0 + (uint32_t)(k * NCH);
+        const uint64_t di = di32;
         Desc d0, d1;
         d0.bit_start = d0.w1 = d0.w2 = d0.w3 = 0;
         d1 = d0;
         int kind0 = 0, kind1 = 0, hb = 0;
         bool ms_frame = false, istereo = false;
         if (L12) {
-            if (act) {
+            {
                 const Desc dd = load_desc(p.grch + di);
-                if (dd.reset_before() && it != 0)
+                if (dd.reset_before() && k != W.kstart)
                     for (int i = lane; i < 15 * kDStride; i += 32) D[i] = V::zero();
                 // lane = subband: its 12 samples of both channels, into the padded layout the DCT reads
                 const float4* x0 = reinterpret_cast<const float4*>(p.l12_x + di * 384 + lane * 12);
@@ -507,16 +627,16 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                     xr[lane * 19 + 4 * q + 3] = V::pack(a.w, b.w);
                 }
             }
-        } else if (act) {
-            if (lane == 0 && it + 1 < n_iter) load_nz(g + 1, nzn0, nzn1);   // used after requantisation
-            mbar_wait(&W.mbar, it & 1);
+        } else {
+            if (lane == 0 && k + 1 < W.kend) load_nz(di32 + NCH, nzn0, nzn1);   // used when the next granule is fetched
+            mbar_wait(&W.mbar, phase);
             {
                 const uint4 v = W.st_desc[0];
                 d0.bit_start = v.x; d0.w1 = v.y; d0.w2 = v.z; d0.w3 = v.w;
                 const uint4 u = W.st_desc[NCH - 1];
                 d1.bit_start = u.x; d1.w1 = u.y; d1.w2 = u.z; d1.w3 = u.w;
             }
-            if (d0.reset_before() && it != 0) {
+            if (d0.reset_before() && k != W.kstart) {
 #pragma unroll
                 for (int i = 0; i < 9; i++) ovl[i] = V::zero();
                 for (int i = lane; i < 15 * kDStride; i += 32) D[i] = V::zero();
@@ -541,15 +661,15 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                     int e0 = (int)rec0[b] << sh0, e1 = NCH == 2 ? (int)rec1[b] << sh1 : 0;
                     float y0 = g0, y1 = g1;
                     if (max(e0, e1) > 120) {   // rare: the loop of L3_ldexp_q2 takes more than one step
-                        for (; e0 > 120; e0 -= 120) y0 = __fmul_rn(y0, s_ldexp[120]);
-                        for (; e1 > 120; e1 -= 120) y1 = __fmul_rn(y1, s_ldexp[120]);
+                        for (; e0 > 120; e0 -= 120) y0 = __fmul_rn(y0, ldexp_step(120));
+                        for (; e1 > 120; e1 -= 120) y1 = __fmul_rn(y1, ldexp_step(120));
                     }
-                    W.gains[0][b] = b < nsf0 ? __fmul_rn(y0, s_ldexp[e0]) : 0.0f;
-                    if (NCH == 2) W.gains[1][b] = b < nsf1 ? __fmul_rn(y1, s_ldexp[e1]) : 0.0f;
+                    W.gains[b][0] = b < nsf0 ? __fmul_rn(y0, ldexp_step(e0)) : 0.0f;
+                    if (NCH == 2) W.gains[b][NCH - 1] = b < nsf1 ? __fmul_rn(y1, ldexp_step(e1)) : 0.0f;
                 }
             }
-            const float* const scf0 = W.gains[0];
-            const float* const scf1 = W.gains[NCH - 1];
+#define L3B_SCF0(b) W.gains[b][0]
+#define L3B_SCF1(b) W.gains[b][NCH - 1]
             if (istereo) {
                 // ist_pos is per-FRAME scratch in the reference (zeroed at frame start, minimp3.d:1497): what granule 1 of
                 // channel 1 does not transmit keeps granule 0's values, including the top-band entries that granule 0's
@@ -569,14 +689,14 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 const bool ms_now = NCH == 2 && ms_frame && !istereo;
                 const int nz_hi = max(nch0, NCH == 2 ? nch1 : 0);   // chunks (8 coefficients) holding anything non-zero
                 // Fast path without a branch per value: every lane looks its four values up in the mirrored table through
-                // an offset that is masked into the table (|v| <= 127 is what almost all values are), so the lookups of
-                // a trip are independent of each other.  Lanes holding a larger value note the trip in `bigmask` and redo
-                // it afterwards through the general path.
-                // byte offset of s_pow43[v + 128] for -128 <= v <= 127 is 4v + 512 = ((4v) & 0x3FC) ^ 0x200; any other v
-                // lands somewhere inside the table (and is redone below)
+                // an offset that is masked into the table (almost all values lie in [-256, 255]), so the lookups of a trip
+                // are independent of each other.  A lane that meets a larger value redoes the trips concerned afterwards
+                // through the general path.  The loop stays rolled (instruction-cache footprint) and runs on pointers.
+                // byte offset of s_pow43[v & 511] is (4v) & 0x7FC; a value outside [-256, 255] lands somewhere inside the
+                // table (and is redone below)
                 const char* const tab = reinterpret_cast<const char*>(s_pow43);
                 uint32_t bigmask = 0;
-#pragma unroll
+#pragma unroll kRqUnroll
                 for (int m = 0; m < 9; m++) {
                     const int pi = lane + 32 * m;
                     if (8 * m >= nz_hi) {   // warp-uniform: both channels are zero from here on (+0.0, like the memset grbuf)
@@ -588,16 +708,16 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                     }
                     const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;   // chunks past nz_chunks were never fetched
                     const uint32_t vb = (NCH == 2 && (pi >> 2) < nch1) ? isw1[pi] : 0u;
-                    const float sa = scf0[W.sfbpair[kind0][pi]];
-                    const float sb = NCH == 2 ? scf1[W.sfbpair[kind1][pi]] : 0.0f;
-                    // a 16-bit value lies in [-128, 127] iff its bits 15..7 are all equal
-                    const uint32_t wide = ((va ^ (va << 1)) | (vb ^ (vb << 1))) & 0xFF00FF00u;
+                    const float sa = L3B_SCF0(W.sfbpair[kind0][pi]);
+                    const float sb = NCH == 2 ? L3B_SCF1(W.sfbpair[kind1][pi]) : 0.0f;
+                    // a 16-bit value lies in [-256, 255] iff its bits 15..8 are all equal
+                    const uint32_t wide = ((va ^ (va << 1)) | (vb ^ (vb << 1))) & 0xFE00FE00u;
                     bigmask |= (wide ? 1u : 0u) << m;
-                    float a0 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((((int)(va << 16) >> 14) & 0x3FC) ^ 0x200)), sa);
-                    float a1 = __fmul_rn(*reinterpret_cast<const float*>(tab + (((((int)va >> 16) << 2) & 0x3FC) ^ 0x200)), sa);
+                    float a0 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((va << 2) & 0x7FCu)), sa);
+                    float a1 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((va >> 14) & 0x7FCu)), sa);
                     if (NCH == 2) {
-                        float b0 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((((int)(vb << 16) >> 14) & 0x3FC) ^ 0x200)), sb);
-                        float b1 = __fmul_rn(*reinterpret_cast<const float*>(tab + (((((int)vb >> 16) << 2) & 0x3FC) ^ 0x200)), sb);
+                        float b0 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((vb << 2) & 0x7FCu)), sb);
+                        float b1 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((vb >> 14) & 0x7FCu)), sb);
                         if (TAPS && mode == 2) {
                             p.tap_xr[di * 576 + 2 * pi] = a0; p.tap_xr[di * 576 + 2 * pi + 1] = a1;
                             p.tap_xr[(di + 1) * 576 + 2 * pi] = b0; p.tap_xr[(di + 1) * 576 + 2 * pi + 1] = b1;
@@ -613,116 +733,31 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                         *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(a0, a1);
                     }
                 }
-                if (bigmask) {   // rare: |v| > 127 somewhere in this lane's coefficients
-#pragma unroll 1
-                    for (int m = 0; m < 9; m++) {
-                        if (!((bigmask >> m) & 1u)) continue;
-                        const int pi = lane + 32 * m;
-                        const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;
-                        const float sa = scf0[W.sfbpair[kind0][pi]];
-                        float a0 = requant(s_pow43, (int)(int16_t)(va & 0xFFFFu), sa);
-                        float a1 = requant(s_pow43, (int)(int16_t)(va >> 16), sa);
-                        if (NCH == 2) {
-                            const uint32_t vb = (pi >> 2) < nch1 ? isw1[pi] : 0u;
-                            const float sb = scf1[W.sfbpair[kind1][pi]];
-                            float b0 = requant(s_pow43, (int)(int16_t)(vb & 0xFFFFu), sb);
-                            float b1 = requant(s_pow43, (int)(int16_t)(vb >> 16), sb);
-                            if (TAPS && mode == 2) {
-                                p.tap_xr[di * 576 + 2 * pi] = a0; p.tap_xr[di * 576 + 2 * pi + 1] = a1;
-                                p.tap_xr[(di + 1) * 576 + 2 * pi] = b0; p.tap_xr[(di + 1) * 576 + 2 * pi + 1] = b1;
-                            }
-                            if (ms_now) {
-                                const float l0 = __fadd_rn(a0, b0), r0 = __fsub_rn(a0, b0);
-                                const float l1 = __fadd_rn(a1, b1), r1 = __fsub_rn(a1, b1);
-                                a0 = l0; b0 = r0; a1 = l1; b1 = r1;
-                            }
-                            *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(a0, b0, a1, b1);
-                        } else {
-                            if (TAPS && mode == 2) { p.tap_xr[di * 576 + 2 * pi] = a0; p.tap_xr[di * 576 + 2 * pi + 1] = a1; }
-                            *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(a0, a1);
-                        }
-                    }
-                }
+                // rare: a value outside [-256, 255] somewhere in this lane's coefficients -- those trips again, through the general
+                // path (out of line, like the intensity stereo pass)
+                if (bigmask)
+                    requant_wide<NCH, TAPS>(W, xr, p.t.pow43, bigmask, nch0, nch1, kind0, kind1, ms_now, lane, TAPS && mode == 2 ? p.tap_xr + di * 576 : nullptr);
             }
             __syncwarp();
             // the staging buffers are free again: fetch the next granule while this one is transformed
-            if (lane == 0 && it + 1 < n_iter) {
+            if (lane == 0 && k + 1 < W.kend) {
                 fence_proxy_async();   // generic -> async proxy ordering of the staging buffers
-                prefetch(g + 1, nzn0, nzn1);
+                prefetch(di32 + NCH, nzn0, nzn1);
             }
 
             // ---------------- intensity stereo (minimp3.d:898-982), on channel 0's band layout ----------------
-            if (NCH == 2 && istereo) {
-                float2* X = reinterpret_cast<float2*>(xr);
-                const int n_long_sfb0 = kind0 == 0 ? 22 : (kind0 == 1 ? 0 : (mpeg1 ? 8 : 6));
-                const int n_sfb0 = n_long_sfb0 + (kind0 == 0 ? 0 : (kind0 == 1 ? 39 : 30));
-                const uint8_t* sfbw = p.t.sfb_width + (row * 3 + kind0) * 40;
-                const uint16_t* sfbo = p.t.sfb_start + (row * 3 + kind0) * 40;
-                int mb0 = -1, mb1 = -1, mb2 = -1;
-                for (int i = lane; i < n_sfb0; i += 32) {  // L3_stereo_top_band
-                    const int off = __ldg(sfbo + i), wdt = __ldg(sfbw + i);
-                    bool nz = false;
-                    for (int k = 0; k < wdt; k++) nz |= (X[off + k].y != 0.0f);
-                    if (nz) { int c = i % 3; if (c == 0) mb0 = max(mb0, i); else if (c == 1) mb1 = max(mb1, i); else mb2 = max(mb2, i); }
-                }
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) {
-                    mb0 = max(mb0, __shfl_xor_sync(0xffffffffu, mb0, sft));
-                    mb1 = max(mb1, __shfl_xor_sync(0xffffffffu, mb1, sft));
-                    mb2 = max(mb2, __shfl_xor_sync(0xffffffffu, mb2, sft));
-                }
-                if (n_long_sfb0) mb0 = mb1 = mb2 = max(max(mb0, mb1), mb2);
-                if (lane == 0) {
-                    const int max_blocks = kind0 == 0 ? 1 : 3;
-                    const int default_pos = mpeg1 ? 3 : 0;
-                    const int mb[3] = {mb0, mb1, mb2};
-                    for (int i = 0; i < max_blocks; i++) {
-                        int itop = n_sfb0 - max_blocks + i, prev = itop - max_blocks;
-                        W.ist[itop] = (uint8_t)(mb[i] >= prev ? default_pos : W.ist[prev]);
-                    }
-                }
-                __syncwarp();
-                const unsigned max_pos = mpeg1 ? 7u : 64u;
-                const int mpeg2_sh = d1.scalefac_compress() & 1;
-                for (int i = lane; i < n_sfb0; i += 32) {  // L3_stereo_process: per-sfb decision and gains
-                    const unsigned ipos = W.ist[i];
-                    const int mbc = (i % 3) == 0 ? mb0 : ((i % 3) == 1 ? mb1 : mb2);
-                    uint8_t md = 0;
-                    if (i > mbc && ipos < max_pos) {
-                        float kl, kr, s = (hb & 2) ? 1.41421356f : 1.0f;
-                        if (mpeg1) {
-                            kl = c_pan[2 * ipos];
-                            kr = c_pan[2 * ipos + 1];
-                        } else {
-                            kl = 1.0f;
-                            kr = ldexp_q2(1.0f, (int)((ipos + 1) >> 1 << mpeg2_sh));
-                            if (ipos & 1) { kl = kr; kr = 1.0f; }
-                        }
-                        W.kl[i] = kl * s;
-                        W.kr[i] = kr * s;
-                        md = 1;
-                    } else if (hb & 2) {
-                        md = 2;
-                    }
-                    W.smode[i] = md;
-                }
-                __syncwarp();
-                for (int m = 0; m < 18; m++) {
-                    const int k = lane + 32 * m;
-                    const int sfb = W.sfbpair[kind0][k >> 1];
-                    const int md = W.smode[sfb];
-                    const float2 v = X[k];
-                    if (md == 1) X[k] = make_float2(__fmul_rn(v.x, W.kl[sfb]), __fmul_rn(v.x, W.kr[sfb]));
-                    else if (md == 2) X[k] = make_float2(__fadd_rn(v.x, v.y), __fsub_rn(v.x, v.y));
-                }
-                __syncwarp();
+            // (out of line: the granule loop's instruction stream stays short and contiguous for the streams without it)
+            if constexpr (NCH == 2) {
+                if (istereo)
+                    intensity_stereo(W, reinterpret_cast<float2*>(xr), kind0, mpeg1, hb, d1.scalefac_compress() & 1,
+                                     p.t.sfb_width + (row * 3 + kind0) * 40, p.t.sfb_start + (row * 3 + kind0) * 40, lane);
             }
             // A MONO frame whose header has the intensity bit set (mode_extension is "don't care" outside joint stereo,
             // but HDR_TEST_I_STEREO looks at the bit in every mode, minimp3.d:100, 1207): the reference runs
             // L3_intensity_stereo on (this channel, a zeroed second channel, zeroed ist_pos): every band is "intensity"
             // with position 0, so the spectrum is multiplied by kl*s -- g_pan[0] = 0 in MPEG-1 (the frame goes silent,
             // signed zeros included), 1 in MPEG-2 -- with s = sqrt(2) when the MS bit is set too (minimp3.d:928-961).
-            if (NCH == 1 && (hb & 1)) {
+            if (NCH == 1 && hb & 1) {
                 const float s = (hb & 2) ? 1.41421356f : 1.0f;
                 const float k = __fmul_rn(mpeg1 ? c_pan[0] : 1.0f, s);
                 float* X = reinterpret_cast<float*>(xr);
@@ -737,10 +772,9 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 }
             }
         }
-        L3B_PHASE_SYNC1();  // phase alignment only (every warp owns its buffers): keeps the CTA on one code region
 
         // ---------------- reorder + antialias + IMDCT + frequency inversion (minimp3.d:1215-1229) ----------
-        if (!L12 && act) {
+        if (!L12) {
             T x[18], y[18];
             const int bt0 = d0.block_type(), bt1 = d1.block_type();
             const int nlb0 = kind0 == 2 ? n_long_bands_mixed : 0, nlb1 = kind1 == 2 ? n_long_bands_mixed : 0;
@@ -789,11 +823,13 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             // closes a mixed run keeps the normal window in its lowest bands.  Only then does the row differ from lane to
             // lane; everywhere else it is warp-uniform, and the window weights stay uniform constant-bank operands.
             const bool stop_mixed = (bt0 == 3 && d0.mixed()) || (NCH == 2 && bt1 == 3 && d1.mixed());
-            if (!stop_mixed && (NCH == 1 || sh0 == sh1)) {
+            const bool same_row = NCH == 1 || (bt0 == 3) == (bt1 == 3);
+            const int wrow = bt0 == 3 ? 18 : 0;   // window row of the long transform: 0 normal / start, 1 stop
+            if (!stop_mixed && (NCH == 1 || sh0 == sh1) && (sh0 || same_row)) {
                 if (sh0) imdct_short_band<V>(x, ovl, y);
-                else imdct36_band<V>(x, ovl, bt0 == 3 ? 1 : 0, bt1 == 3 ? 1 : 0, y);
+                else imdct36_band<V>(x, ovl, wrow, y);
             } else {
-                // Rare: the channels use different transforms in this band, or the window row is per lane.  The
+                // Rare: the channels use different transforms or window rows in this band, or the row is per lane.  The
                 // out-of-line helper works on COPIES so that x / ovl / y themselves never have their address taken
                 // (they must stay in registers).
                 const int ws0 = (bt0 == 3 && lane >= (d0.mixed() ? n_long_bands_mixed : 0)) ? 1 : 0;
@@ -821,10 +857,9 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 }
             }
         }
-        L3B_PHASE_SYNC2();
 
         // ---------------- DCT-32 matrixing across bands, one time slot per lane (minimp3.d:1232-1298) -------
-        if (act && mode >= 1 && lane < NS) {
+        if (mode >= 1 && lane < NS) {
             T t[4][8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -889,19 +924,15 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
         __syncwarp();   // (a CTA barrier here measured slower; the warp's own writes must still be ordered before the window's reads)
 
         // ---------------- 512-tap window (minimp3.d:1305-1406) ----------------
-        if (act && mode == 2) {
-            constexpr long long kGranFrames = 32 * NS;   // 576 (Layer III) / 384 (Layer I / II)
-            const uint64_t f0 = (uint64_t)g * (uint64_t)kGranFrames;   // first frame of this granule in the decoded signal
+        if (mode == 2) {
             // samples [lo, hi) of this granule are delivered (all of them except at the edges of the stream's PCM range)
-            const long long rel = (long long)skipf - (long long)f0;
-            const int dlo = (int)max(0ll, min(kGranFrames, rel));
-            const int dhi = (int)max(0ll, min(kGranFrames, rel + (long long)countf));
+            const int dlo = max(0, min((int)kGranFrames, W.rel_lo0 - k * (int)kGranFrames));
+            const int dhi = max(0, min((int)kGranFrames, W.rel_hi0 - k * (int)kGranFrames));
             const unsigned span = (unsigned)(dhi - dlo);
 #define L3B_DELIVER(f) ((unsigned)((f) - dlo) < span)
             // frame 0 of this granule in the delivered signal (only dereferenced for delivered frames); one byte pointer per
             // granule, compile-time offsets from there: a store is a range test and a predicated STG
-            constexpr int kFrameBytes = NCH * (S16 ? 2 : 4);
-            char* const gbase = out_base + ((long long)f0 - (long long)skipf) * kFrameBytes;
+            char* const gbase = W.tbase + (long long)k * (kGranFrames * kFrameBytes);
             const float scale = 1.0f / 32768.0f;
             // 16-bit delivery: q = clamp(lrintf(x * 32768), -32768, 32767) of the float sample x the float path would
             // have written (the conversion SURVEY 8c defines; un-dithered, wav.d:475-700)
@@ -1009,7 +1040,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
         }
 #undef L3B_DELIVER
         // slide the history: the last 15 slots become rows 0..14 (qmf_state, minimp3.d:1423-1433)
-        if (act && mode >= 1) {
+        if (mode >= 1) {
             __syncwarp();
             if (NCH == 2) {
                 // 15 x 33 float2 = 495 elements moved down by 18 rows.  D is 8 bytes past a 16-byte boundary, and so is
@@ -1052,7 +1083,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
 template <int NCH, int WARPS, bool FUSED, bool TAPS, bool S16, bool L12>
 static cudaError_t launch_granule_t(const BatchParams& p, const Tile* tiles, uint32_t n, cudaStream_t s) {
     if (!n) return cudaSuccess;
-    const size_t smem = kCtaTableBytes + (size_t)WARPS * sizeof(WarpSmem<NCH>);
+    const size_t smem = (size_t)WARPS * sizeof(WarpSmem<NCH>);   // + kCtaTableBytes of static tables
     // the attribute is per device and a process may hold contexts on several: set it every time (a cheap driver call)
     cudaError_t e = cudaFuncSetAttribute(l3_granule_kernel<NCH, WARPS, FUSED, TAPS, S16, L12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
