@@ -267,6 +267,21 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
         return L3B_E_PARAM;
     }
     if (b->n_grch >= (1ull << 31)) { c->err = "more than 2^31 granule-channels in one batch; split it into waves"; return L3B_E_PARAM; }
+    // Granules per warp tile of the granule kernel.  Every tile recomputes a halo of two or three granules, so long tiles
+    // waste less (128: 16.8 ms, 64: 16.9 ms on BASELINE config 2), but a batch needs a couple of tiles per resident warp to
+    // fill the device and a lone stream is decoded sooner in short ones: the longest of 128 / 64 / 32 / 16 that still gives
+    // two tiles per warp slot (16 warps per SM), else 16.
+    uint32_t tile_granules = 16;
+    {
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < b->n_streams; i++) {
+            const l3b_stream_desc_t& s = b->streams[i];
+            const uint64_t per = ((s.layer == 1 || s.layer == 2) ? 384u : 576u) * (uint64_t)(s.nch == 2 ? 2 : 1);
+            if (s.pcm_count) total += (s.pcm_skip + s.pcm_count + per - 1) / per - s.pcm_skip / per;
+        }
+        for (uint32_t t = (uint32_t)kTileGranulesMax; t > 16; t >>= 1)
+            if (total / t >= 2ull * 16ull * (uint64_t)c->sms) { tile_granules = t; break; }
+    }
     // validate stream table and build the tile lists
     std::vector<Tile> tiles[4];
     uint64_t expect_grch = 0;
@@ -287,8 +302,8 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
         if (!s.pcm_count) continue;
         const uint64_t per = gran * s.nch;
         uint32_t g0 = (uint32_t)(s.pcm_skip / per), g1 = (uint32_t)((s.pcm_skip + s.pcm_count + per - 1) / per);
-        for (uint32_t g = g0; g < g1; g += kTileGranules)
-            tiles[(l12 ? 2 : 0) + (s.nch == 2 ? 0 : 1)].push_back({i, g, std::min<uint32_t>(kTileGranules, g1 - g)});
+        for (uint32_t g = g0; g < g1; g += tile_granules)
+            tiles[(l12 ? 2 : 0) + (s.nch == 2 ? 0 : 1)].push_back({i, g, std::min<uint32_t>(tile_granules, g1 - g)});
     }
     if (expect_grch != b->n_grch) { c->err = "n_grch does not match the stream table"; return L3B_E_PARAM; }
     // sub-batches: cut at stream boundaries into up to kMaxSubs pieces of similar size (>= 64 K granule-channels each)

@@ -31,6 +31,23 @@ struct Desc {
     __device__ __forceinline__ int kind() const { return block_type() == 2 ? (mixed() ? 2 : 1) : 0; }
 };
 
+// What the granule kernel needs of a descriptor, packed into one word of the scalefactor record by l3_scf_kernel.
+struct GranFlags {
+    uint32_t v;
+    static __device__ __forceinline__ uint32_t pack(const Desc& d) {
+        return (uint32_t)d.block_type() | ((uint32_t)d.mixed() << 2) | ((uint32_t)d.scalefac_scale() << 3) | ((uint32_t)d.second_granule() << 4) |
+               ((uint32_t)(d.scalefac_compress() & 1) << 5) | ((uint32_t)d.hdr_bits() << 6) | ((uint32_t)d.reset_before() << 10);
+    }
+    __device__ __forceinline__ int block_type() const { return v & 3; }
+    __device__ __forceinline__ int mixed() const { return (v >> 2) & 1; }
+    __device__ __forceinline__ int scalefac_scale() const { return (v >> 3) & 1; }
+    __device__ __forceinline__ int second_granule() const { return (v >> 4) & 1; }
+    __device__ __forceinline__ int scalefac_compress_lsb() const { return (v >> 5) & 1; }
+    __device__ __forceinline__ int hdr_bits() const { return (v >> 6) & 15; }
+    __device__ __forceinline__ int reset_before() const { return (v >> 10) & 1; }
+    __device__ __forceinline__ int kind() const { return block_type() == 2 ? (mixed() ? 2 : 1) : 0; }
+};
+
 __device__ __forceinline__ Desc load_desc(const l3b_grch_desc_t* p) {
     uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
     Desc d;

@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(128) l3_scf_kernel(BatchParams p) {
         const bool ms_frame = (d.hdr_bits() & 0xE) == 0x6;   // HDR_IS_MS_STEREO: the 1/sqrt(2) of MS stereo is folded in here
         const int gain_exp = d.global_gain() - 4 - 210 - (ms_frame ? 2 : 0);
         recw[kSfGainOff / 4] = __float_as_uint(ldexp_q2(2048.0f, 44 - gain_exp));
+        recw[kSfFlagsOff / 4] = GranFlags::pack(d);
         uint4* dst = wstage + lane * kRecRow;
 #pragma unroll
         for (int i = 0; i < kSfRecBytes / 16; i++) dst[i] = make_uint4(recw[4 * i], recw[4 * i + 1], recw[4 * i + 2], recw[4 * i + 3]);

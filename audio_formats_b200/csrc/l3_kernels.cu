@@ -160,11 +160,12 @@ __device__ __noinline__ float pow43_big(const float* pow43, int x) {
     return __ldg(pow43 + ((x + sign) >> 6)) * (1.0f + frac * ((4.0f / 3) + frac * (2.0f / 9))) * (float)mult;
 }
 
-// General path (a value outside the 9-bit range of the shared table somewhere in the lane's words): |v|^(4/3) from the positive table in global memory
-// (129 entries, minimp3.d:722-725) or L3_pow_43's interpolation, then the sign.  (-p)*s == -(p*s) exactly.
-__device__ __forceinline__ float requant(const float* pow43g, int v, float s) {
-    const int a = v < 0 ? -v : v;
-    const float r = __fmul_rn(a <= 128 ? __ldg(pow43g + a) : pow43_big(pow43g, a), s);
+// General path (a value outside the 9-bit range of the shared table somewhere in the lane's trip): the values inside the
+// range from the shared table all the same, the others through L3_pow_43's interpolation (positive table of 129 entries in
+// global memory, minimp3.d:722-725, 737-745), then the sign.  (-p)*s == -(p*s) exactly.
+__device__ __forceinline__ float requant(const float* pow43s, const float* pow43g, int v, float s) {
+    if ((unsigned)(v + 256) < 512u) return __fmul_rn(pow43s[v & 511], s);
+    const float r = __fmul_rn(pow43_big(pow43g, v < 0 ? -v : v), s);
     return v < 0 ? -r : r;
 }
 
@@ -329,7 +330,6 @@ struct __align__(16) WarpSmem {
     uint4 st_is[NCH * kIsChunks];              // TMA-staged inputs of the next granule: quantised spectra (only the chunks
                                                //   that hold anything: `nz_chunks` of each channel),
     uint4 st_rec[NCH * kSfRecBytes / 16];      //   scalefactor records,
-    uint4 st_desc[NCH];                        //   descriptors
     float gains[40][NCH];                      // band gains of this granule (minimp3.d:714-719), the channels of a band adjacent
     uint8_t sfbpair[3][288];
     uint8_t ist[40];
@@ -414,23 +414,22 @@ __device__ __noinline__ void intensity_stereo(WarpSmem<2>& W, float2* X, int kin
 // Requantisation through the general path (minimp3.d:813-816, 737-745, 874-878 + MS stereo :885-896) for the trips of this
 // lane flagged in `bigmask`: a value outside the shared table's range.  tap_xr: the granule's row of the xr snapshot or null.
 template <int NCH, bool TAPS>
-__device__ __noinline__ void requant_wide(WarpSmem<NCH>& W, typename VT<NCH, false>::T* xr, const float* pow43g, uint32_t bigmask, int nch0, int nch1,
+__device__ __noinline__ void requant_wide(WarpSmem<NCH>& W, typename VT<NCH, false>::T* xr, const float* pow43s, const float* pow43g, uint32_t bigmask, int nch0, int nch1,
                                           int kind0, int kind1, bool ms_now, int lane, float* tap_xr) {
     const uint32_t* isw0 = reinterpret_cast<const uint32_t*>(W.st_is);
     const uint32_t* isw1 = isw0 + (NCH - 1) * (kIsChunks * 4);
 #pragma unroll 1
-    for (int m = 0; m < 9; m++) {
-        if (!((bigmask >> m) & 1u)) continue;
-        const int pi = lane + 32 * m;
+    for (; bigmask; bigmask &= bigmask - 1u) {
+        const int pi = lane + 32 * (__ffs((int)bigmask) - 1);
         const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;
         const float sa = W.gains[W.sfbpair[kind0][pi]][0];
-        float a0 = requant(pow43g, (int)(int16_t)(va & 0xFFFFu), sa);
-        float a1 = requant(pow43g, (int)(int16_t)(va >> 16), sa);
+        float a0 = requant(pow43s, pow43g, (int)(int16_t)(va & 0xFFFFu), sa);
+        float a1 = requant(pow43s, pow43g, (int)(int16_t)(va >> 16), sa);
         if (NCH == 2) {
             const uint32_t vb = (pi >> 2) < nch1 ? isw1[pi] : 0u;
             const float sb = W.gains[W.sfbpair[kind1][pi]][NCH - 1];
-            float b0 = requant(pow43g, (int)(int16_t)(vb & 0xFFFFu), sb);
-            float b1 = requant(pow43g, (int)(int16_t)(vb >> 16), sb);
+            float b0 = requant(pow43s, pow43g, (int)(int16_t)(vb & 0xFFFFu), sb);
+            float b1 = requant(pow43s, pow43g, (int)(int16_t)(vb >> 16), sb);
             if (TAPS && tap_xr) {
                 tap_xr[2 * pi] = a0; tap_xr[2 * pi + 1] = a1;
                 tap_xr[576 + 2 * pi] = b0; tap_xr[576 + 2 * pi + 1] = b1;
@@ -577,11 +576,10 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
     // hold anything are fetched: n0 / n1 = nz_chunks of the two channels (from p.nzc, read a granule ahead).
     auto prefetch = [&](uint32_t di32, uint32_t n0, uint32_t n1) {
         const uint64_t di = di32;
-        mbar_expect_tx(&W.mbar, (n0 + n1) * 16u + NCH * (kSfRecBytes + 16));
+        mbar_expect_tx(&W.mbar, (n0 + n1) * 16u + NCH * kSfRecBytes);
         if (n0) tma_load_1d(W.st_is, p.is + di * kIsChunks, n0 * 16u, &W.mbar);
         if (NCH == 2 && n1) tma_load_1d(W.st_is + kIsChunks, p.is + (di + 1) * kIsChunks, n1 * 16u, &W.mbar);
         tma_load_1d(W.st_rec, p.sf + di * kSfRecBytes, NCH * kSfRecBytes, &W.mbar);
-        tma_load_1d(W.st_desc, p.grch + di, NCH * 16, &W.mbar);
     };
     auto load_nz = [&](uint32_t di32, uint32_t& n0, uint32_t& n1) {
         const uint8_t* q = p.nzc + di32;
@@ -605,9 +603,8 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
         const int mode = k >= 0 ? 2 : ((L12 || k == -1) ? 1 : 0);
         const uint32_t di32 = di0 + (uint32_t)(k * NCH);
         const uint64_t di = di32;
-        Desc d0, d1;
-        d0.bit_start = d0.w1 = d0.w2 = d0.w3 = 0;
-        d1 = d0;
+        GranFlags d0, d1;   // the descriptor bits of the two channels (from the records)
+        d0.v = d1.v = 0;
         int kind0 = 0, kind1 = 0, hb = 0;
         bool ms_frame = false, istereo = false;
         if (L12) {
@@ -630,12 +627,8 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
         } else {
             if (lane == 0 && k + 1 < W.kend) load_nz(di32 + NCH, nzn0, nzn1);   // used when the next granule is fetched
             mbar_wait(&W.mbar, phase);
-            {
-                const uint4 v = W.st_desc[0];
-                d0.bit_start = v.x; d0.w1 = v.y; d0.w2 = v.z; d0.w3 = v.w;
-                const uint4 u = W.st_desc[NCH - 1];
-                d1.bit_start = u.x; d1.w1 = u.y; d1.w2 = u.z; d1.w3 = u.w;
-            }
+            d0.v = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(W.st_rec) + kSfFlagsOff);
+            d1.v = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(W.st_rec) + (NCH - 1) * kSfRecBytes + kSfFlagsOff);
             if (d0.reset_before() && k != W.kstart) {
 #pragma unroll
                 for (int i = 0; i < 9; i++) ovl[i] = V::zero();
@@ -713,11 +706,15 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                     // a 16-bit value lies in [-256, 255] iff its bits 15..8 are all equal
                     const uint32_t wide = ((va ^ (va << 1)) | (vb ^ (vb << 1))) & 0xFE00FE00u;
                     bigmask |= (wide ? 1u : 0u) << m;
-                    float a0 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((va << 2) & 0x7FCu)), sa);
-                    float a1 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((va >> 14) & 0x7FCu)), sa);
+                    float a0 = *reinterpret_cast<const float*>(tab + ((va << 2) & 0x7FCu));
+                    float a1 = *reinterpret_cast<const float*>(tab + ((va >> 14) & 0x7FCu));
                     if (NCH == 2) {
-                        float b0 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((vb << 2) & 0x7FCu)), sb);
-                        float b1 = __fmul_rn(*reinterpret_cast<const float*>(tab + ((vb >> 14) & 0x7FCu)), sb);
+                        float b0 = *reinterpret_cast<const float*>(tab + ((vb << 2) & 0x7FCu));
+                        float b1 = *reinterpret_cast<const float*>(tab + ((vb >> 14) & 0x7FCu));
+                        {   // both channels of a coefficient in one packed multiply (two independent roundings, like two FMULs)
+                            const float2 u0 = __fmul2_rn(make_float2(a0, b0), make_float2(sa, sb)), u1 = __fmul2_rn(make_float2(a1, b1), make_float2(sa, sb));
+                            a0 = u0.x; b0 = u0.y; a1 = u1.x; b1 = u1.y;
+                        }
                         if (TAPS && mode == 2) {
                             p.tap_xr[di * 576 + 2 * pi] = a0; p.tap_xr[di * 576 + 2 * pi + 1] = a1;
                             p.tap_xr[(di + 1) * 576 + 2 * pi] = b0; p.tap_xr[(di + 1) * 576 + 2 * pi + 1] = b1;
@@ -729,6 +726,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                         }
                         *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(a0, b0, a1, b1);
                     } else {
+                        a0 = __fmul_rn(a0, sa); a1 = __fmul_rn(a1, sa);
                         if (TAPS && mode == 2) { p.tap_xr[di * 576 + 2 * pi] = a0; p.tap_xr[di * 576 + 2 * pi + 1] = a1; }
                         *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(a0, a1);
                     }
@@ -736,7 +734,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 // rare: a value outside [-256, 255] somewhere in this lane's coefficients -- those trips again, through the general
                 // path (out of line, like the intensity stereo pass)
                 if (bigmask)
-                    requant_wide<NCH, TAPS>(W, xr, p.t.pow43, bigmask, nch0, nch1, kind0, kind1, ms_now, lane, TAPS && mode == 2 ? p.tap_xr + di * 576 : nullptr);
+                    requant_wide<NCH, TAPS>(W, xr, s_pow43, p.t.pow43, bigmask, nch0, nch1, kind0, kind1, ms_now, lane, TAPS && mode == 2 ? p.tap_xr + di * 576 : nullptr);
             }
             __syncwarp();
             // the staging buffers are free again: fetch the next granule while this one is transformed
@@ -749,7 +747,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             // (out of line: the granule loop's instruction stream stays short and contiguous for the streams without it)
             if constexpr (NCH == 2) {
                 if (istereo)
-                    intensity_stereo(W, reinterpret_cast<float2*>(xr), kind0, mpeg1, hb, d1.scalefac_compress() & 1,
+                    intensity_stereo(W, reinterpret_cast<float2*>(xr), kind0, mpeg1, hb, d1.scalefac_compress_lsb(),
                                      p.t.sfb_width + (row * 3 + kind0) * 40, p.t.sfb_start + (row * 3 + kind0) * 40, lane);
             }
             // A MONO frame whose header has the intensity bit set (mode_extension is "don't care" outside joint stereo,

@@ -22,14 +22,13 @@
 
 namespace l3b {
 
-constexpr int kSfRecBytes = 96;    // per granule-channel: iscf[40] ist_pos[40] nz_chunks(u16) pad[2] gain(f32) pad[8]
+constexpr int kSfRecBytes = 96;    // per granule-channel: iscf[40] ist_pos[40] nz_chunks(u16) pad[2] gain(f32) flags(u32) pad[4]
 constexpr int kSfGainOff = 84;     // byte offset of the granule-channel gain 2^(gain_exp/4) (minimp3.d:714-716) inside the record;
                                    // the 40 band gains are one table multiplication each in the granule kernel
+constexpr int kSfFlagsOff = 88;    // byte offset of the descriptor bits the granule kernel needs (GranFlags, l3_desc.cuh): with them in
+                                   // the record the kernel stages one thing less per granule
 constexpr int kIsChunks = 72;      // 576 int16 = 72 x 16 bytes
-#ifndef L3B_TILE_GRANULES
-#define L3B_TILE_GRANULES 64
-#endif
-constexpr int kTileGranules = L3B_TILE_GRANULES;  // granules per warp tile of the granule kernel (2-granule recompute halo)
+constexpr int kTileGranulesMax = 128;   // longest warp tile of the granule kernel, in granules (l3b_batch_create picks 16 .. 128 per batch)
 constexpr int kXrStride = 608;     // spectrum buffer elements: 576 in natural layout / 32x19 in the padded layout
 
 struct Tile {
