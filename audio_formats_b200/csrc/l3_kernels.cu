@@ -856,6 +856,8 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             }
         }
 
+        __syncwarp();   // the transform's rows (lane = subband) are read by columns (lane = time slot) from here on
+
         // ---------------- DCT-32 matrixing across bands, one time slot per lane (minimp3.d:1232-1298) -------
         if (mode >= 1 && lane < NS) {
             T t[4][8];
