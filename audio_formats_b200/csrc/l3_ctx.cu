@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,10 @@ struct l3b_ctx {
     int last_launches = 0;
     int sms = 148;                    // multiprocessors of THIS device (grid sizing of the persistent Huffman kernels)
     cudaEvent_t ev_wait = nullptr;    // cudaEventBlockingSync: host waits sleep instead of spinning (one core per waiting lane otherwise)
+    // one recycled stream workspace: an AudioStream that closes leaves its device buffers here for the next one that opens
+    // (a dozen cudaMalloc / cudaFree calls cost more than decoding a short file)
+    std::mutex spare_mutex;
+    struct l3b_resident* spare = nullptr;
 };
 
 // Wait for everything queued on the context stream without burning a core: a pipeline keeps several lanes per GPU
@@ -175,6 +180,7 @@ int l3b_ctx_create(int device_id, l3b_ctx_t** out) {
 void l3b_ctx_destroy(l3b_ctx_t* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->spare) { l3b_batch_free(c, c->spare); c->spare = nullptr; }
     if (c->d_tables) cudaFree(c->d_tables);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -711,6 +717,20 @@ int l3b_decode_scans(l3b_ctx_t* c, l3b_scan_t* const* scans, uint32_t n, float* 
 namespace l3b {
 int resident_for_device_inputs(l3b_ctx_t* c, const l3b_batch_t* shape, l3b_resident_t** inout) { return upload_impl(c, shape, inout, false, true); }
 uint8_t* resident_blob(l3b_resident_t* r) { return r->d_blob; }
+l3b_resident_t* ctx_take_spare_workspace(l3b_ctx_t* c) {
+    std::lock_guard<std::mutex> g(c->spare_mutex);
+    l3b_resident_t* r = c->spare;
+    c->spare = nullptr;
+    return r;
+}
+void ctx_give_spare_workspace(l3b_ctx_t* c, l3b_resident_t* r) {
+    if (!r) return;
+    {
+        std::lock_guard<std::mutex> g(c->spare_mutex);
+        if (!c->spare) { c->spare = r; return; }
+    }
+    l3b_batch_free(c, r);
+}
 l3b_grch_desc_t* resident_descs(l3b_resident_t* r) { return r->d_grch; }
 const uint8_t* ctx_sfb_width(l3b_ctx_t* c) { return c->t.sfb_width; }
 cudaStream_t ctx_stream(l3b_ctx_t* c) { return c->stream; }

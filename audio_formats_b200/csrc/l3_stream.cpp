@@ -14,6 +14,11 @@
 
 using namespace l3b;
 
+namespace l3b {   // l3_ctx.cu: one recycled stream workspace per context
+l3b_resident_t* ctx_take_spare_workspace(l3b_ctx_t* c);
+void ctx_give_spare_workspace(l3b_ctx_t* c, l3b_resident_t* r);
+}
+
 namespace {
 // Frames walked (and decoded in one batch) per refill.  Large on purpose: a refill costs one upload, four launches and one
 // download whatever its size, and 64 frames are two warps' worth of work on a 148-SM part.  2,048 frames are 53 s of
@@ -45,7 +50,7 @@ struct l3b_stream {
     l3b_resident_t* workspace = nullptr;  // device buffers recycled across decode-ahead windows
 
     ~l3b_stream() {
-        if (workspace) l3b_batch_free(ctx, workspace);
+        if (workspace) ctx_give_spare_workspace(ctx, workspace);   // the next stream of this context starts with these buffers
         delete reader;
     }
 };
@@ -110,6 +115,7 @@ static int decode_pending(l3b_stream* s) {
     b.n_streams = 1;
     b.pcm = s->cache.data() + old;
     b.pcm_floats = sd.pcm_count;
+    if (!s->workspace) s->workspace = ctx_take_spare_workspace(s->ctx);
     int rc = l3b_batch_upload_reuse(s->ctx, &b, &s->workspace);
     if (!rc) rc = l3b_batch_run(s->ctx, s->workspace);
     if (!rc) rc = l3b_batch_download(s->ctx, s->workspace, b.pcm, 0, b.pcm_floats);
