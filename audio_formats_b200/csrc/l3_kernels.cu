@@ -474,7 +474,8 @@ __device__ __noinline__ void imdct_split(float* x, float* ovl, float* y, bool sh
     else imdct36_band<V1>(x, ovl, 18 * ws0, y);
 }
 
-constexpr int kCtaTableBytes = 2048 + 2048;   // s_pow43 (512 floats) | s_win (16 x 32 floats)
+constexpr int kWinStride = 20;                // floats per lane in s_win: 16 weights + 4 (rows of 80 bytes: conflict-free 16-byte loads)
+constexpr int kCtaTableBytes = 2048 + 32 * kWinStride * 4;   // s_pow43 (512 floats) | s_win (32 lanes x 20 floats)
 
 // L12: the Layer I / II instance -- a granule is 12 slots x 32 subbands whose samples arrive dequantised and scaled from
 // l12_parse_kernel (p.l12_x); only the synthesis half of the pipeline runs (minimp3.d:1567 calls mp3d_synth_granule with 12).
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
     // tables shared by the CTA, statically allocated (their shared-memory addresses are compile-time constants, so a lookup
     // is LDS [offset register + constant])
     __shared__ __align__(16) float s_pow43[512];   // 512 signed entries
-    __shared__ __align__(16) float s_win[16 * 32];   // synthesis window weights per lane: [tap k][w0 / w1][lane]
+    __shared__ __align__(16) float s_win[32 * kWinStride];   // synthesis window weights per lane: [lane][tap k][w0 / w1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSmem<NCH>& W = *reinterpret_cast<WarpSmem<NCH>*>(smem_raw + (size_t)warp * sizeof(WarpSmem<NCH>));
     T* const D = W.Dbuf + 1;
@@ -519,8 +520,8 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
     // and fetched at the start of every window stage: held in registers across the IMDCT they cost 16 registers there.
     const int ii = lane & 15, par = lane >> 4;
     for (int i = threadIdx.x; i < 16 * 32; i += 32 * WARPS) {
-        const int l = i & 31, kc = i >> 5;
-        s_win[i] = (l & 15) < 15 ? __ldg(p.t.win + kc * 15 + (l & 15)) : 0.0f;
+        const int l = i >> 4, kc = i & 15;
+        s_win[l * kWinStride + kc] = (l & 15) < 15 ? __ldg(p.t.win + kc * 15 + (l & 15)) : 0.0f;
     }
 #ifdef L3B_EXP_W_REGS   // A/B only: weights held in registers for the whole kernel
     float w0[8], w1[8];
@@ -954,9 +955,9 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
 #ifndef L3B_EXP_W_REGS
                 float w0[8], w1[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    w0[k] = s_win[(2 * k) * 32 + lane];
-                    w1[k] = s_win[(2 * k + 1) * 32 + lane];
+                for (int k = 0; k < 4; k++) {   // four 16-byte loads
+                    const float4 w = *reinterpret_cast<const float4*>(&s_win[lane * kWinStride + 4 * k]);
+                    w0[2 * k] = w.x; w1[2 * k] = w.y; w0[2 * k + 1] = w.z; w1[2 * k + 1] = w.w;
                 }
 #endif
                 // lane (par, ii) produces samples 15-ii and 17+ii of slots s = 2q + par.
@@ -972,7 +973,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 char* pa = gbase + fa * kFrameBytes;
                 char* pb = gbase + fb * kFrameBytes;
 #pragma unroll 1
-                for (int q3 = 0; q3 < NS / 6; q3++, fa += 192, fb += 192, pa += 192 * kFrameBytes, pb += 192 * kFrameBytes) {
+                for (int q3 = 0;; q3++, fa += 192, fb += 192, pa += 192 * kFrameBytes, pb += 192 * kFrameBytes) {
                     const T* lo = base_lo + q3 * 6 * kDStride;
                     const T* hi = base_hi + q3 * 6 * kDStride;
 #pragma unroll
@@ -1004,6 +1005,7 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                         if (L3B_DELIVER(fa + 64 * qq)) store(pa + 64 * qq * kFrameBytes, a);
                         if (L3B_DELIVER(fb + 64 * qq)) store(pb + 64 * qq * kFrameBytes, b);
                     }
+                    if (q3 == NS / 6 - 1) break;   // (nothing to slide after the last trip)
 #pragma unroll
                     for (int j = 0; j < 16; j++) Vw[j] = Vw[j + 6];   // slide by three slots
                 }

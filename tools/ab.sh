@@ -1,5 +1,7 @@
 #!/bin/bash
 # usage: ab.sh name1=lib1 name2=lib2 ... ; prints step, entropy, granule ms (bit-exact) per library variant ("default" = product library)
+# CAUTION: the product library is rebuilt on import whenever a source is newer than it -- on the GPU box "default" is therefore the
+# WORKING TREE, not the last commit.  Compare explicit variants (tools/variant.py base, built before editing) unless the tree is clean.
 for kv in "$@"; do
   name=${kv%%=*}; lib=${kv#*=}
   if [ "$lib" = "default" ]; then unset L3B_LIB; else export L3B_LIB=$PWD/$lib; fi
