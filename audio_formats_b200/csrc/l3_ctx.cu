@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/l3b200.h"
+
 #include "l3_device_tables.hpp"
 #include "l3_host.hpp"
 #include "l3_kernels.cuh"
@@ -278,8 +279,9 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     // fill the device and a lone stream is decoded sooner in short ones: the longest of 128 / 64 / 32 / 16 that still gives
     // two tiles per warp slot (16 warps per SM), else 16.
     uint32_t tile_granules = 16;
+    uint64_t total_granules = 0;
     {
-        uint64_t total = 0;
+        uint64_t& total = total_granules;
         for (uint32_t i = 0; i < b->n_streams; i++) {
             const l3b_stream_desc_t& s = b->streams[i];
             const uint64_t per = ((s.layer == 1 || s.layer == 2) ? 384u : 576u) * (uint64_t)(s.nch == 2 ? 2 : 1);
@@ -290,7 +292,7 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
     }
     // validate stream table and build the tile lists
     std::vector<Tile> tiles[4];
-    uint64_t expect_grch = 0;
+    uint64_t expect_grch = 0, granules_before = 0;
     bool has_l12 = false;
     for (uint32_t i = 0; i < b->n_streams; i++) {
         const l3b_stream_desc_t& s = b->streams[i];
@@ -308,8 +310,15 @@ static int upload_impl(l3b_ctx_t* c, const l3b_batch_t* b, l3b_resident_t** inou
         if (!s.pcm_count) continue;
         const uint64_t per = gran * s.nch;
         uint32_t g0 = (uint32_t)(s.pcm_skip / per), g1 = (uint32_t)((s.pcm_skip + s.pcm_count + per - 1) / per);
-        for (uint32_t g = g0; g < g1; g += tile_granules)
-            tiles[(l12 ? 2 : 0) + (s.nch == 2 ? 0 : 1)].push_back({i, g, std::min<uint32_t>(tile_granules, g1 - g)});
+        // The tiles are taken in table order, one per warp, and a warp that starts late finishes late: the last eighth of the
+        // batch goes into half-length tiles and the last twentieth into quarter-length ones, so that the device drains in a
+        // quarter of a tile's time instead of a whole one (the extra halo granules cost less than the idle SMs did).
+        uint32_t tg = tile_granules;
+        if (granules_before * 20 >= total_granules * 19) tg = std::max(16u, tile_granules / 4);
+        else if (granules_before * 8 >= total_granules * 7) tg = std::max(16u, tile_granules / 2);
+        granules_before += g1 - g0;
+        for (uint32_t g = g0; g < g1; g += tg)
+            tiles[(l12 ? 2 : 0) + (s.nch == 2 ? 0 : 1)].push_back({i, g, std::min<uint32_t>(tg, g1 - g)});
     }
     if (expect_grch != b->n_grch) { c->err = "n_grch does not match the stream table"; return L3B_E_PARAM; }
     // sub-batches: cut at stream boundaries into up to kMaxSubs pieces of similar size (>= 64 K granule-channels each)
