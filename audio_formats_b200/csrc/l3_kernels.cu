@@ -690,16 +690,20 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                 // table (and is redone below)
                 const char* const tab = reinterpret_cast<const char*>(s_pow43);
                 uint32_t bigmask = 0;
-#pragma unroll kRqUnroll
-                for (int m = 0; m < 9; m++) {
+                // trips m >= mhi hold nothing in either channel (+0.0, like the memset grbuf): their own short loop, so that
+                // the loop over the trips that hold something has no test in it
+                const int mhi = min(9, (nz_hi + 7) >> 3);
+#pragma unroll 1
+                for (int m = mhi; m < 9; m++) {
                     const int pi = lane + 32 * m;
-                    if (8 * m >= nz_hi) {   // warp-uniform: both channels are zero from here on (+0.0, like the memset grbuf)
-                        if (NCH == 2) *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        else *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(0.0f, 0.0f);
-                        if (TAPS && mode == 2)
-                            for (int c = 0; c < NCH; c++) p.tap_xr[(di + c) * 576 + 2 * pi] = p.tap_xr[(di + c) * 576 + 2 * pi + 1] = 0.0f;
-                        continue;
-                    }
+                    if (NCH == 2) *reinterpret_cast<float4*>(&xr[2 * pi]) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    else *reinterpret_cast<float2*>(&xr[2 * pi]) = make_float2(0.0f, 0.0f);
+                    if (TAPS && mode == 2)
+                        for (int c = 0; c < NCH; c++) p.tap_xr[(di + c) * 576 + 2 * pi] = p.tap_xr[(di + c) * 576 + 2 * pi + 1] = 0.0f;
+                }
+#pragma unroll kRqUnroll
+                for (int m = 0; m < mhi; m++) {
+                    const int pi = lane + 32 * m;
                     const uint32_t va = (pi >> 2) < nch0 ? isw0[pi] : 0u;   // chunks past nz_chunks were never fetched
                     const uint32_t vb = (NCH == 2 && (pi >> 2) < nch1) ? isw1[pi] : 0u;
                     const float sa = L3B_SCF0(W.sfbpair[kind0][pi]);
