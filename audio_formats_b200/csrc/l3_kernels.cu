@@ -784,6 +784,36 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
             if (kind0 == 0 && kind1 == 0) {
 #pragma unroll
                 for (int i = 0; i < 18; i++) x[i] = xr[lane * 18 + i];
+                // alias reduction across all 31 band boundaries (minimp3.d:1002-1020): the neighbours' elements are read
+                // from the buffer (eight adjacent elements each: 16-byte loads for stereo) instead of being shuffled in one
+                // by one.  Lanes 0 / 31 read eight elements outside the spectrum (inside the warp's buffer) and drop them.
+                T dnv[8], upv[8];   // band-1: elements 10..17, band+1: elements 0..7
+                if (NCH == 2) {
+                    const float4* dq = reinterpret_cast<const float4*>(xr + (lane - 1) * 18 + 10);
+                    const float4* uq = reinterpret_cast<const float4*>(xr + (lane + 1) * 18);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float4 a = dq[q], b = uq[q];
+                        dnv[2 * q] = V::pack(a.x, a.y); dnv[2 * q + 1] = V::pack(a.z, a.w);
+                        upv[2 * q] = V::pack(b.x, b.y); upv[2 * q + 1] = V::pack(b.z, b.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { dnv[i] = xr[(lane - 1) * 18 + 10 + i]; upv[i] = xr[(lane + 1) * 18 + i]; }
+                }
+                const bool lo = lane >= 1, up = lane < 31;
+                T nlo[8], nhi[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    nlo[i] = V::mm_sub(x[i], c_aa[i], dnv[7 - i], c_aa[8 + i]);
+                    nhi[i] = V::mm_add(upv[i], c_aa[8 + i], x[17 - i], c_aa[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    x[i] = V::sel(lo, lo, nlo[i], x[i]);
+                    x[17 - i] = V::sel(up, up, nhi[i], x[17 - i]);
+                }
+                __syncwarp();  // every lane has its inputs in registers: the buffer may be rewritten in the padded (x19) layout
             } else {
                 // short / mixed blocks: L3_reorder folded into the load through the permutation table
                 const uint16_t* pm0 = p.t.perm + (row * 2 + (kind0 == 2 ? 1 : 0)) * 576 + lane * 18;
@@ -799,25 +829,25 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) l3_granule_kernel(Batc
                         x[i] = V::pack(xf[i0], 0.0f);
                     }
                 }
-            }
-            __syncwarp();  // every lane has its inputs in registers: the buffer may be rewritten in the padded (x19) layout,
-                           // and the stores below are free to interleave with the transform
-            const int aa0 = kind0 == 0 ? 31 : nlb0 - 1, aa1 = kind1 == 0 ? 31 : nlb1 - 1;
-            if (aa0 > 0 || aa1 > 0) {
-                const bool lo0 = lane >= 1 && lane - 1 < aa0, up0 = lane < aa0;
-                const bool lo1 = lane >= 1 && lane - 1 < aa1, up1 = lane < aa1;
-                T nlo[8], nhi[8];
+                __syncwarp();  // every lane has its inputs in registers: the buffer may be rewritten in the padded (x19) layout,
+                               // and the stores below are free to interleave with the transform
+                const int aa0 = kind0 == 0 ? 31 : nlb0 - 1, aa1 = kind1 == 0 ? 31 : nlb1 - 1;
+                if (aa0 > 0 || aa1 > 0) {
+                    const bool lo0 = lane >= 1 && lane - 1 < aa0, up0 = lane < aa0;
+                    const bool lo1 = lane >= 1 && lane - 1 < aa1, up1 = lane < aa1;
+                    T nlo[8], nhi[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const T dn = V::shfl_up(x[17 - i]);   // band-1, element 17-i
-                    const T up = V::shfl_down(x[i]);      // band+1, element i
-                    nlo[i] = V::mm_sub(x[i], c_aa[i], dn, c_aa[8 + i]);
-                    nhi[i] = V::mm_add(up, c_aa[8 + i], x[17 - i], c_aa[i]);
-                }
+                    for (int i = 0; i < 8; i++) {
+                        const T dn = V::shfl_up(x[17 - i]);   // band-1, element 17-i
+                        const T up = V::shfl_down(x[i]);      // band+1, element i
+                        nlo[i] = V::mm_sub(x[i], c_aa[i], dn, c_aa[8 + i]);
+                        nhi[i] = V::mm_add(up, c_aa[8 + i], x[17 - i], c_aa[i]);
+                    }
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    x[i] = V::sel(lo0, lo1, nlo[i], x[i]);
-                    x[17 - i] = V::sel(up0, up1, nhi[i], x[17 - i]);
+                    for (int i = 0; i < 8; i++) {
+                        x[i] = V::sel(lo0, lo1, nlo[i], x[i]);
+                        x[17 - i] = V::sel(up0, up1, nhi[i], x[17 - i]);
+                    }
                 }
             }
             const bool sh0 = bt0 == 2 && lane >= nlb0, sh1 = bt1 == 2 && lane >= nlb1;
