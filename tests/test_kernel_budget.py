@@ -46,3 +46,23 @@ def test_granule_loop_span_fits_the_instruction_cache(built):
             span = max(span, int(addr, 16) - int(m.group(1), 16))
     # measured: 2,987 instructions (47 KB) -> 17.6 ms with luck in the layout, 2,222 -> 17.3 ms whatever the layout; 16 bytes each
     assert 0 < span // 16 <= 2400, span // 16
+
+
+def test_alias_reduction_neighbour_reads_stay_inside_the_warp_buffer():
+    """Long-block granules read the neighbouring bands' eight elements straight from the spectrum buffer (l3_kernels.cu,
+    "alias reduction across all 31 band boundaries"): lane 0 reads eight elements below the spectrum, lane 31 eight above its
+    576 coefficients, both dropped afterwards.  Those reads must stay inside the warp's own Dbuf and be 16-byte aligned for
+    the stereo instance (float2 elements, float4 loads).  Pins the layout constants the kernel relies on."""
+    src = (ROOT / "audio_formats_b200" / "csrc" / "l3_kernels.cu").read_text()
+    hdr = (ROOT / "audio_formats_b200" / "csrc" / "l3_kernels.cuh").read_text()
+    stride = int(re.search(r"constexpr int kDStride = (\d+);", src).group(1))
+    xr_len = int(re.search(r"constexpr int kXrStride = (\d+);", hdr).group(1))
+    assert re.search(r"Dbuf\[1 \+ 15 \* kDStride \+ kXrStride\]", src), "WarpSmem::Dbuf layout changed"
+    xr0 = 1 + 15 * stride                      # index of xr[0] inside Dbuf (D = Dbuf + 1, xr = D + 15 rows)
+    total = 1 + 15 * stride + xr_len
+    for lane in range(32):
+        dn = xr0 + (lane - 1) * 18 + 10        # band-1, elements 10..17
+        up = xr0 + (lane + 1) * 18             # band+1, elements 0..7
+        assert 0 <= dn and dn + 8 <= total, (lane, dn)
+        assert 0 <= up and up + 8 <= total, (lane, up)
+        assert (dn * 8) % 16 == 0 and (up * 8) % 16 == 0, (lane, dn, up)   # float2 elements, Dbuf is 16-byte aligned
